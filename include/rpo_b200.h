@@ -1,0 +1,142 @@
+/*
+ * rpo_b200 — C ABI of the B200-native RPO projection hot path.
+ *
+ * The reference (wadx2019/rpo) is pure Python/torch and has no FFI; its de-facto plug-in boundary is the
+ * duck-typed "hard-constraint protocol" that rpo.algo calls on an environment plus the grad_steps loop
+ * (SURVEY.md §8b).  Every entry point below replaces one of those methods; the reference file:line it
+ * replaces is cited on each declaration (paths relative to the reference root).
+ *
+ * Conventions
+ *   - all array arguments are DEVICE pointers to row-major float32 (int32 for status/flags), unless the
+ *     function name ends in _host; rows are contiguous except `state`, which carries a leading dimension
+ *     `ld_state` (in floats) so that a (B,57) observation tensor or a (B,28) [pd|qd] slice can be passed;
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream, allocates
+ *     nothing and never synchronises;
+ *   - return value 0 = ok, negative = error (RPO_ERR_*); rpo_last_error() gives a message;
+ *   - a pointer documented "nullable" may be NULL to skip that output.
+ */
+#ifndef RPO_B200_H
+#define RPO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RPO_OK 0
+#define RPO_ERR_INVALID_ARG (-1)
+#define RPO_ERR_CUDA (-2)
+
+/* per-instance status word written by the completion kernels (optional output) */
+#define RPO_STATUS_ITERS_MASK 0xff       /* Newton iterations used */
+#define RPO_STATUS_NOT_CONVERGED 0x100   /* ||delta||_2 >= tol after max_iters (reference: `converged`, evopf.py:837, discarded) */
+#define RPO_STATUS_SMALL_PIVOT 0x200     /* |pivot| < 1e-6 in the static-order LU (reference: torch.inverse would raise on singular) */
+
+/* EVOPF-v0 dimensions (evopf.py:270-337) */
+#define RPO_EVOPF_STATE_DIM 57
+#define RPO_EVOPF_X_DIM 28
+#define RPO_EVOPF_Y_DIM 43
+#define RPO_EVOPF_Z_DIM 14
+#define RPO_EVOPF_EQ_NUM 28
+#define RPO_EVOPF_INEQ_NUM 58
+
+int rpo_version(void);
+const char* rpo_last_error(void);
+/* name of the compiled SM target, e.g. "sm_100a" */
+const char* rpo_build_arch(void);
+
+/* ------------------------------------------------------------------ EVOPF-v0 ---------------------------------- */
+
+/* EVOPFEnv.complete_partial -> PFFunctionFn.forward            rpo/env/electrical_grid/evopf.py:724-727, 789-855
+ * state: rows hold [pd(14) | qd(14) | ...] (only the first 28 floats of a row are read); z (B,14); y (B,43) out.
+ * tol/max_iters: Newton stop rule (reference: 1e-5 / 50, evopf.py:786).  status: nullable (B) int32. */
+int rpo_evopf_complete_fwd(const float* state, int ld_state, const float* z, float* y, int64_t B, float tol,
+                           int max_iters, int32_t* status, void* stream);
+
+/* PFFunctionFn.backward (GRG / implicit-function backward)      rpo/env/electrical_grid/evopf.py:857-910
+ * y (B,43) = output of the forward; dl_dy (B,43); dl_dz (B,14) out; dl_dx (B,28) out, nullable.
+ * The Jacobian is recomputed from y (the reference saves (B,28,43)+(B,22,22) tensors, evopf.py:851-853). */
+int rpo_evopf_complete_bwd(const float* y, const float* dl_dy, float* dl_dz, float* dl_dx, int64_t B, void* stream);
+
+/* EVOPFEnv.ineq_partial_grad (reduced correction direction)     rpo/env/electrical_grid/evopf.py:596-612
+ * state rows: [pd|qd|soc(5)|...] (first 33 floats read); y (B,43); out (B,43). */
+int rpo_evopf_direction(const float* state, int ld_state, const float* y, float* out, int64_t B, void* stream);
+
+/* RPODDPG.grad_steps / RPOSAC.grad_steps, corr_mode == 0        rpo/algo/rpo_ddpg.py:266-305, rpo/algo/rpo_sac.py:280-319
+ * Runs exactly n_steps correction steps on every instance (y_out may alias y_in).  unsat_flags (n_steps int32,
+ * nullable) is zeroed by the call and unsat_flags[k] is set to 1 when ANY instance fails the loop test
+ * (max|eq_resid| > corr_eps or max ineq_dist > corr_eps) before step k — the host uses it to reproduce the
+ * reference's global-max loop exit (see rpo_b200/algo.py). */
+int rpo_evopf_correct(const float* state, int ld_state, const float* y_in, float* y_out, int64_t B, float lr,
+                      float momentum, float corr_eps, int n_steps, int32_t* unsat_flags, void* stream);
+
+/* RPODDPG.process_action = complete_partial + grad_steps fused  rpo/algo/rpo_ddpg.py:72-77 (no-grad call sites :100,:106,:330)
+ * y (B,43) nullable: completion output before correction; y_corr (B,43): corrected action. */
+int rpo_evopf_project(const float* state, int ld_state, const float* z, float* y, float* y_corr, int64_t B, float tol,
+                      int max_iters, float lr, float momentum, float corr_eps, int n_steps, int32_t* unsat_flags,
+                      int32_t* status, void* stream);
+
+/* EVOPFEnv.eq_resid / ineq_resid                                 rpo/env/electrical_grid/evopf.py:520-546, 548-563 (+Battery.ineq_resid :104-121)
+ * eq (B,28) nullable; ineq (B,58) nullable (ineq_dist = max(ineq, 0)). */
+int rpo_evopf_resid(const float* state, int ld_state, const float* y, float* eq, float* ineq, int64_t B, void* stream);
+
+/* EVOPFEnv.step, batched row-wise                                rpo/env/electrical_grid/evopf.py:348-366 (+Battery.step :74-102, obj_fn :509-518)
+ * state (B,57); y (B,43) action; next_exo (B,52) = next [pd|qd](28) + next price window (24) from the data loaders;
+ * next_state (B,57) out; reward (B) out; eq_viol (B,28) nullable; ineq_viol (B,58) nullable (both at the pre-step state). */
+int rpo_evopf_step(const float* state, const float* y, const float* next_exo, float* next_state, float* reward,
+                   float* eq_viol, float* ineq_viol, int64_t B, void* stream);
+
+/* ------------------------------------------------------------------ Safe Cartpole ----------------------------- */
+/* partial_idx in {0,1}: which force is the policy output (CartSafeEnv.partial_actions is drawn at random at
+ * construction, rpo/env/classic_control/cartpole.py:117). */
+
+/* CartSafeEnv.complete_partial                                   rpo/env/classic_control/cartpole.py:369-373 ; z (B,1) -> a (B,2) */
+int rpo_cart_complete_fwd(const float* z, float* a, int64_t B, int partial_idx, void* stream);
+/* autograd of the above: dl_da (B,2) -> dl_dz (B,1) */
+int rpo_cart_complete_bwd(const float* dl_da, float* dl_dz, int64_t B, int partial_idx, void* stream);
+/* CartSafeEnv.ineq_partial_grad                                  cartpole.py:396-408 */
+int rpo_cart_direction(const float* a, float* out, int64_t B, int partial_idx, void* stream);
+/* grad_steps on CartSafeEnv                                      rpo/algo/rpo_ddpg.py:266-305 */
+int rpo_cart_correct(const float* a_in, float* a_out, int64_t B, int partial_idx, float lr, float momentum,
+                     float corr_eps, int n_steps, int32_t* unsat_flags, void* stream);
+/* fused complete + correct */
+int rpo_cart_project(const float* z, float* a, float* a_corr, int64_t B, int partial_idx, float lr, float momentum,
+                     float corr_eps, int n_steps, int32_t* unsat_flags, void* stream);
+/* CartSafeEnv.eq_resid / ineq_resid                              cartpole.py:375-379 ; eq (B,1), ineq (B,6), nullable */
+int rpo_cart_resid(const float* a, float* eq, float* ineq, int64_t B, void* stream);
+/* CartSafeEnv.step, batched row-wise                             cartpole.py:166-229 ; state (B,6), a (B,2) ->
+ * next_state (B,6), done (B) int32, eq_viol (B,1) / ineq_viol (B,6) nullable (unclipped action). */
+int rpo_cart_step(const float* state, const float* a, float* next_state, int32_t* done, float* eq_viol, float* ineq_viol,
+                  int64_t B, void* stream);
+
+/* ------------------------------------------------------------------ Spring Pendulum --------------------------- */
+/* obs (B,5) = [cos th, sin th, thdot, l, ldot]; the policy output is fx (partial_actions = [0], pendulum.py:48).
+ * Row-wise semantics: each row is evaluated as the reference evaluates a batch of one. */
+
+/* SpringPendulumEnv.complete_partial (+ set_eq)                  rpo/env/classic_control/pendulum.py:256-288 */
+int rpo_pen_complete_fwd(const float* obs, const float* z, float* a, int64_t B, void* stream);
+int rpo_pen_complete_bwd(const float* obs, const float* dl_da, float* dl_dz, int64_t B, void* stream);
+/* SpringPendulumEnv.ineq_partial_grad                            pendulum.py:331-343 */
+int rpo_pen_direction(const float* obs, const float* a, float* out, int64_t B, void* stream);
+int rpo_pen_correct(const float* obs, const float* a_in, float* a_out, int64_t B, float lr, float momentum,
+                    float corr_eps, int n_steps, int32_t* unsat_flags, void* stream);
+int rpo_pen_project(const float* obs, const float* z, float* a, float* a_corr, int64_t B, float lr, float momentum,
+                    float corr_eps, int n_steps, int32_t* unsat_flags, void* stream);
+/* SpringPendulumEnv.eq_resid / ineq_resid                        pendulum.py:298-303 ; eq (B,1), ineq (B,1), nullable */
+int rpo_pen_resid(const float* obs, const float* a, float* eq, float* ineq, int64_t B, void* stream);
+/* SpringPendulumEnv.step, batched row-wise                       pendulum.py:80-128 ; st (B,4) = (th, thdot, l, ldot), a (B,2) ->
+ * next_st (B,4), next_obs (B,5), reward (B), done (B) int32, eq_viol (B,1) / ineq_viol (B,1) nullable. */
+int rpo_pen_step(const float* st, const float* a, float* next_st, float* next_obs, float* reward, int32_t* done,
+                 float* eq_viol, float* ineq_viol, int64_t B, void* stream);
+
+/* ------------------------------------------------------------------ measurement helpers ----------------------- */
+/* Dependency-free FP32 FMA micro-kernel used by bench.py to measure the FP32 roofline denominator on the box
+ * (SURVEY.md §8d).  Launches `blocks` x `threads`, `iters` x 8 independent FMA chains x 4 per thread; out (blocks*threads) floats.
+ * flops executed = 2 * 32 * iters * blocks * threads. */
+int rpo_fp32_peak_probe(float* out, int blocks, int threads, int iters, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RPO_B200_H */

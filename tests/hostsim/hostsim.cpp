@@ -1,0 +1,53 @@
+// Host-side simulator of the per-instance device code — TEST INFRASTRUCTURE ONLY.
+// Compiles rpo_b200/csrc/{evopf,classic}_core.cuh with g++ (RPO_REAL = float or double) so the CPU test-suite
+// can check the generated math against the oracle where no GPU exists.  Never loaded by rpo_b200/.
+#include <stdint.h>
+#include "../../rpo_b200/csrc/evopf_core.cuh"
+#include "../../rpo_b200/csrc/classic_core.cuh"
+
+extern "C" {
+
+void hs_evopf_complete(const real* state, int ld, const real* z, real* y, int B, real tol, int max_iters, int* status) {
+    for (int b = 0; b < B; ++b) {
+        int st = evopf_complete(state + (long)b * ld, z + (long)b * 14, y + (long)b * 43, tol, max_iters, RpoVoteSelf());
+        if (status) status[b] = st;
+    }
+}
+
+void hs_evopf_backward(const real* y, const real* g, real* dz, real* dx, int B) {
+    for (int b = 0; b < B; ++b)
+        evopf_backward(y + (long)b * 43, g + (long)b * 43, dz + (long)b * 14, dx ? dx + (long)b * 28 : (real*)0);
+}
+
+void hs_evopf_direction(const real* state, int ld, const real* y, real* out, real* eqmax, real* ineqmax, int B) {
+    for (int b = 0; b < B; ++b)
+        evopf_direction(state + (long)b * ld, state + (long)b * ld + 28, y + (long)b * 43, out + (long)b * 43,
+                        eqmax + b, ineqmax + b);
+}
+
+// flags[k] |= 1 if any instance fails the loop test before step k (k = 0..n_steps-1)
+void hs_evopf_correct(const real* state, int ld, real* y, int B, real lr, real momentum, real corr_eps, int n_steps,
+                      int* flags) {
+    for (int b = 0; b < B; ++b) {
+        real prev[43];
+        for (int i = 0; i < 43; ++i) prev[i] = 0;
+        for (int k = 0; k < n_steps; ++k) {
+            real mp;
+            bool unsat = evopf_correct_step<true>(state + (long)b * ld, state + (long)b * ld + 28, y + (long)b * 43,
+                                                  prev, lr, momentum, corr_eps, &mp);
+            if (unsat && flags) flags[k] = 1;
+        }
+    }
+}
+
+void hs_evopf_resid(const real* state, int ld, const real* y, real* eq, real* ineq, int B) {
+    for (int b = 0; b < B; ++b) {
+        EvopfPt pt;
+        evopf_eval_flows(y + (long)b * 43, pt);
+        evopf_eq_resid(state + (long)b * ld, y + (long)b * 43, pt, eq + (long)b * 28);
+        evopf_ineq(state + (long)b * ld + 28, y + (long)b * 43, ineq + (long)b * 58, (real*)0);
+    }
+}
+
+int hs_sizeof_real() { return (int)sizeof(real); }
+}

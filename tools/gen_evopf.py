@@ -1,0 +1,600 @@
+#!/usr/bin/env python
+"""Code generator for the per-instance EVOPF math (writes rpo_b200/csrc/evopf_gen.cuh).
+
+The IEEE-14 network is fixed, so the sparsity pattern of the power-flow Jacobian, a fill-reducing
+elimination order and every index map are known at build time.  This script performs the symbolic
+work once (pattern, minimum-degree bus ordering, symbolic LU with fill) and emits straight-line
+`__host__ __device__` code over locally-scoped arrays with literal indices, which nvcc scalarises
+into registers: no pivot search, no index arithmetic, no zero multiplications, all network
+constants folded into FFMA immediates.
+
+Math (derivation in DESIGN.md §3; reference lines in rpo/env/electrical_grid/evopf.py):
+  flows   P_i = vr_i a_i + vi_i b_i, Q_i = vi_i a_i - vr_i b_i, a + jb = Y (vr + j vi)   (:520-546)
+  T1_ij = vr_i al_ij + vi_i be_ij, T2_ij = vi_i al_ij - vr_i be_ij, al + j be = Y_ij (vr_j + j vi_j)
+  scaled flow Jacobian F (V-columns multiplied by V_j), i != j:
+      dP_i/dth_j = T2_ij   V_j dP_i/dV_j = T1_ij   dQ_i/dth_j = -T1_ij   V_j dQ_i/dV_j = T2_ij
+  i == j:  T2_ii - Q_i,    T1_ii + P_i,            P_i - T1_ii,          T2_ii + Q_i                (:614-661)
+  reference Jacobian: J[:, va_j] = -F[:, th_j], J[:, vm_j] = -F[:, V_j] / V_j.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from rpo_b200 import evopf_constants as K  # noqa: E402
+
+
+def lit(x: float) -> str:
+    """f32-rounded literal wrapped in RC() so the same header can be compiled in double for validation."""
+    v = float(np.float32(x))
+    return "RC(%.9g)" % v
+
+
+class Gen(object):
+    def __init__(self):
+        self.G = K.G.astype(np.float32).astype(np.float64)
+        self.B = K.B.astype(np.float32).astype(np.float64)
+        nb = K.NBUS
+        self.nb = nb
+        self.nz = [[j for j in range(nb) if (self.G[i, j] != 0 or self.B[i, j] != 0)] for i in range(nb)]
+        self.kidx = {}
+        for i in range(nb):
+            for j in self.nz[i]:
+                self.kidx[(i, j)] = len(self.kidx)
+        self.nnz = len(self.kidx)
+        assert np.allclose(K.G, K.G.T) and np.allclose(K.B, K.B.T), "symmetric Y-bus expected"
+        self.slack = int(K.SLACK[0])
+        self.spv = [int(v) for v in K.SPV]
+        self.pv = [int(v) for v in K.PV]
+        self.pq = [int(v) for v in K.PQ]
+        self.order = self.min_degree_order()
+        self.unk, self.eqs = [], []
+        for b in self.order:
+            self.unk.append(("th", b))
+            self.eqs.append(("P", b))
+            if b in self.pq:
+                self.unk.append(("V", b))
+                self.eqs.append(("Q", b))
+        self.n = len(self.unk)
+        assert self.n == 22
+        self.symbolic()
+        self.out = []
+
+    # ---------------------------------------------------------------- symbolic work
+    def min_degree_order(self):
+        nodes = [b for b in range(self.nb) if b != self.slack]
+        adj = {b: set(j for j in self.nz[b] if j != b and j != self.slack) for b in nodes}
+        weight = {b: (2 if b in self.pq else 1) for b in nodes}
+        order = []
+        while adj:
+            # minimise the fill-in flops of eliminating b: sum of neighbour weights (ties: lowest id)
+            b = min(adj, key=lambda v: (sum(weight[u] for u in adj[v]), v))
+            nb_ = adj.pop(b)
+            for u in nb_:
+                adj[u].discard(b)
+                adj[u] |= (nb_ - {u})
+            order.append(b)
+        return order
+
+    def symbolic(self):
+        n = self.n
+        pat = [[(self.unk[c][1] in self.nz[self.eqs[r][1]]) for c in range(n)] for r in range(n)]
+        self.orig = [row[:] for row in pat]
+        for k in range(n):
+            assert pat[k][k]
+            for i in range(k + 1, n):
+                if pat[i][k]:
+                    for j in range(k + 1, n):
+                        if pat[k][j]:
+                            pat[i][j] = True
+        self.pat = pat
+        self.luidx = {}
+        for r in range(n):
+            for c in range(n):
+                if pat[r][c]:
+                    self.luidx[(r, c)] = len(self.luidx)
+        self.nlu = len(self.luidx)
+        fl = 0
+        for k in range(n):
+            rows = [i for i in range(k + 1, n) if pat[i][k]]
+            cols = [j for j in range(k + 1, n) if pat[k][j]]
+            fl += len(rows) * (1 + len(cols))
+        self.lu_ops = fl
+        self.nL = sum(1 for (r, c) in self.luidx if r > c)
+        self.nU = sum(1 for (r, c) in self.luidx if r <= c)
+
+    # ---------------------------------------------------------------- expression helpers
+    def F(self, eq, unk, pt="pt."):
+        """C expression of the scaled flow-Jacobian entry F[eq, unk] or None if structurally zero."""
+        (ek, i), (uk, j) = eq, unk
+        if j not in self.nz[i]:
+            return None
+        k = self.kidx[(i, j)]
+        if i != j:
+            return {("P", "th"): "%sT2[%d]" % (pt, k), ("P", "V"): "%sT1[%d]" % (pt, k),
+                    ("Q", "th"): "(-%sT1[%d])" % (pt, k), ("Q", "V"): "%sT2[%d]" % (pt, k)}[(ek, uk)]
+        return {("P", "th"): "%sHd[%d]" % (pt, i), ("P", "V"): "%sNd[%d]" % (pt, i),
+                ("Q", "th"): "%sMd[%d]" % (pt, i), ("Q", "V"): "%sLd[%d]" % (pt, i)}[(ek, uk)]
+
+    def emit(self, s=""):
+        self.out.append(s)
+
+    def accum(self, target, terms, init=None, negate=False):
+        """Emit target = init (+|-) sum(a*b) as an FMA chain.  terms: list of (exprA, exprB)."""
+        sign = "-" if negate else ""
+        if init is None:
+            if not terms:
+                self.emit("    %s = RC(0.0);" % target)
+                return
+            a, b = terms[0]
+            self.emit("    %s = %s(%s) * (%s);" % (target, sign, a, b))
+            terms = terms[1:]
+        else:
+            self.emit("    %s = %s;" % (target, init))
+        for a, b in terms:
+            self.emit("    %s = FMA(%s(%s), (%s), %s);" % (target, sign, a, b, target))
+
+    # ---------------------------------------------------------------- emitters
+    def gen_header(self):
+        e = self.emit
+        e("// GENERATED by tools/gen_evopf.py — do not edit by hand.")
+        e("// Per-instance EVOPF-v0 math over locally scoped arrays with literal indices (see DESIGN.md §3).")
+        e("// elimination order (bus ids, 0-based): %s" % self.order)
+        e("// nnz(Y) = %d, Newton n = %d, nnz(L) = %d, nnz(U) = %d (original nnz(J_N) = %d), LU mul/fma ops = %d"
+          % (self.nnz, self.n, self.nL, self.nU, sum(sum(r) for r in self.orig), self.lu_ops))
+        e("#pragma once")
+        e("#define EVOPF_NNZY %d" % self.nnz)
+        e("#define EVOPF_NN %d" % self.n)
+        e("#define EVOPF_NLU %d" % self.nlu)
+        e("")
+        e("struct EvopfPt {")
+        e("    real vr[14], vi[14];      // rectangular voltages")
+        e("    real P[14], Q[14];        // bus power flows")
+        e("    real T1[EVOPF_NNZY], T2[EVOPF_NNZY];")
+        e("    real Hd[14], Nd[14], Md[14], Ld[14];  // diagonal entries of the scaled flow Jacobian")
+        e("};")
+        e("")
+
+    def gen_eval(self):
+        """evopf_eval<FULL>: sincos, rectangular voltages, flows, and (FULL) the T terms + diagonals."""
+        e = self.emit
+        for full in (0, 1):
+            name = "evopf_eval_full" if full else "evopf_eval_flows"
+            e("// y -> point quantities (%s)" % ("flows + Jacobian terms" if full else "flows only"))
+            e("RPO_HD void %s(const real* y, EvopfPt& pt) {" % name)
+            for i in range(self.nb):
+                e("    { real s_, c_; SINCOS(y[%d], &s_, &c_); pt.vr[%d] = y[%d] * c_; pt.vi[%d] = y[%d] * s_; }"
+                  % (K.VA0 + i, i, K.VM0 + i, i, K.VM0 + i))
+            for i in range(self.nb):
+                e("    {")
+                e("    real a_, b_;")
+                first = True
+                for j in self.nz[i]:
+                    k = self.kidx[(i, j)]
+                    g, b = self.G[i, j], self.B[i, j]
+                    if full:
+                        # al = G vr_j - B vi_j ; be = B vr_j + G vi_j
+                        if g != 0:
+                            e("    const real al%d = FMA(%s, pt.vr[%d], %s * pt.vi[%d]);" % (k, lit(g), j, lit(-b), j))
+                            e("    const real be%d = FMA(%s, pt.vr[%d], %s * pt.vi[%d]);" % (k, lit(b), j, lit(g), j))
+                        else:
+                            e("    const real al%d = %s * pt.vi[%d];" % (k, lit(-b), j))
+                            e("    const real be%d = %s * pt.vr[%d];" % (k, lit(b), j))
+                        if first:
+                            e("    a_ = al%d; b_ = be%d;" % (k, k))
+                        else:
+                            e("    a_ += al%d; b_ += be%d;" % (k, k))
+                        if i != j:
+                            e("    pt.T1[%d] = FMA(pt.vr[%d], al%d, pt.vi[%d] * be%d);" % (k, i, k, i, k))
+                            e("    pt.T2[%d] = FMA(pt.vi[%d], al%d, -(pt.vr[%d] * be%d));" % (k, i, k, i, k))
+                        else:
+                            e("    const real t1d_ = FMA(pt.vr[%d], al%d, pt.vi[%d] * be%d);" % (i, k, i, k))
+                            e("    const real t2d_ = FMA(pt.vi[%d], al%d, -(pt.vr[%d] * be%d));" % (i, k, i, k))
+                    else:
+                        if first:
+                            if g != 0:
+                                e("    a_ = FMA(%s, pt.vr[%d], %s * pt.vi[%d]);" % (lit(g), j, lit(-b), j))
+                                e("    b_ = FMA(%s, pt.vr[%d], %s * pt.vi[%d]);" % (lit(b), j, lit(g), j))
+                            else:
+                                e("    a_ = %s * pt.vi[%d];" % (lit(-b), j))
+                                e("    b_ = %s * pt.vr[%d];" % (lit(b), j))
+                        else:
+                            if g != 0:
+                                e("    a_ = FMA(%s, pt.vr[%d], a_); a_ = FMA(%s, pt.vi[%d], a_);" % (lit(g), j, lit(-b), j))
+                                e("    b_ = FMA(%s, pt.vr[%d], b_); b_ = FMA(%s, pt.vi[%d], b_);" % (lit(b), j, lit(g), j))
+                            else:
+                                e("    a_ = FMA(%s, pt.vi[%d], a_);" % (lit(-b), j))
+                                e("    b_ = FMA(%s, pt.vr[%d], b_);" % (lit(b), j))
+                    first = False
+                e("    pt.P[%d] = FMA(pt.vr[%d], a_, pt.vi[%d] * b_);" % (i, i, i))
+                e("    pt.Q[%d] = FMA(pt.vi[%d], a_, -(pt.vr[%d] * b_));" % (i, i, i))
+                if full:
+                    e("    pt.Hd[%d] = t2d_ - pt.Q[%d]; pt.Nd[%d] = t1d_ + pt.P[%d];" % (i, i, i, i))
+                    e("    pt.Md[%d] = pt.P[%d] - t1d_; pt.Ld[%d] = t2d_ + pt.Q[%d];" % (i, i, i, i))
+                e("    }")
+            e("}")
+            e("")
+
+    def gen_factor(self):
+        e = self.emit
+        n = self.n
+        e("// In-place sparse LU (no pivoting, static order) of the scaled Newton matrix A~ = F[N rows, w cols].")
+        e("// lu[] holds the strict-lower multipliers and U; ipiv[] the pivot reciprocals.  Returns min |pivot|.")
+        e("RPO_HD real evopf_factor(const EvopfPt& pt, real* lu, real* ipiv) {")
+        zero = set()
+        for (r, c), idx in sorted(self.luidx.items(), key=lambda kv: kv[1]):
+            if self.orig[r][c]:
+                e("    lu[%d] = %s;" % (idx, self.F(self.eqs[r], self.unk[c])))
+            else:
+                zero.add((r, c))
+        e("    real minpiv = RC(3.0e38);")
+        for k in range(n):
+            kk = self.luidx[(k, k)]
+            e("    minpiv = FMIN(minpiv, FABS(lu[%d]));" % kk)
+            e("    ipiv[%d] = RCP(lu[%d]);" % (k, kk))
+            rows = [i for i in range(k + 1, n) if self.pat[i][k]]
+            cols = [j for j in range(k + 1, n) if self.pat[k][j]]
+            for i in rows:
+                ik = self.luidx[(i, k)]
+                assert (i, k) not in zero
+                e("    lu[%d] *= ipiv[%d];" % (ik, k))
+                for j in cols:
+                    ij, kj = self.luidx[(i, j)], self.luidx[(k, j)]
+                    assert (k, j) not in zero
+                    if (i, j) in zero:
+                        e("    lu[%d] = -(lu[%d] * lu[%d]);" % (ij, ik, kj))
+                        zero.discard((i, j))
+                    else:
+                        e("    lu[%d] = FMA(-lu[%d], lu[%d], lu[%d]);" % (ij, ik, kj, ij))
+        assert not zero
+        e("    return minpiv;")
+        e("}")
+        e("")
+        # solves
+        e("// x <- A~^{-1} x  (x indexed by elimination position: in = equations, out = unknowns)")
+        e("RPO_HD void evopf_solve(const real* lu, const real* ipiv, real* x) {")
+        for k in range(n):
+            for i in range(k + 1, n):
+                if self.pat[i][k]:
+                    e("    x[%d] = FMA(-lu[%d], x[%d], x[%d]);" % (i, self.luidx[(i, k)], k, i))
+        for k in reversed(range(n)):
+            for j in range(k + 1, n):
+                if self.pat[k][j]:
+                    e("    x[%d] = FMA(-lu[%d], x[%d], x[%d]);" % (k, self.luidx[(k, j)], j, k))
+            e("    x[%d] *= ipiv[%d];" % (k, k))
+        e("}")
+        e("")
+        e("// x <- A~^{-T} x  (in = unknown positions, out = equation positions)")
+        e("RPO_HD void evopf_solve_t(const real* lu, const real* ipiv, real* x) {")
+        # U^T w = b : forward over columns of U
+        for k in range(n):
+            for j in range(k):
+                if self.pat[j][k]:
+                    e("    x[%d] = FMA(-lu[%d], x[%d], x[%d]);" % (k, self.luidx[(j, k)], j, k))
+            e("    x[%d] *= ipiv[%d];" % (k, k))
+        # L^T x = w : backward, unit diagonal
+        for k in reversed(range(n)):
+            for i in range(k + 1, n):
+                if self.pat[i][k]:
+                    e("    x[%d] = FMA(-lu[%d], x[%d], x[%d]);" % (k, self.luidx[(i, k)], i, k))
+        e("}")
+        e("")
+
+    def eq_pos(self, kind, bus):
+        return self.eqs.index((kind, bus))
+
+    def unk_pos(self, kind, bus):
+        return self.unk.index((kind, bus))
+
+    def gen_newton(self):
+        e = self.emit
+        e("// One Newton iteration of the completion (PFFunctionFn.forward evopf.py:826-835): y's Newton unknowns are")
+        e("// updated in place; returns ||delta||_2^2 of the *unscaled* update.  pd/qd = x[0:14], x[14:28].")
+        e("RPO_HD real evopf_newton_iter(const real* x, real* y, EvopfPt& pt, real* minpiv) {")
+        e("    real lu[EVOPF_NLU], ipiv[EVOPF_NN], r[EVOPF_NN];")
+        e("    evopf_eval_full(y, pt);")
+        for k, (kind, i) in enumerate(self.eqs):
+            if kind == "P":
+                if i in self.pv:
+                    g = self.spv.index(i)
+                    e("    r[%d] = ((y[%d] + y[%d]) - x[%d]) - pt.P[%d];" % (k, K.PG0 + g, K.PE0 + g, i, i))
+                else:
+                    e("    r[%d] = (-x[%d]) - pt.P[%d];" % (k, i, i))
+            else:
+                e("    r[%d] = (-x[%d]) - pt.Q[%d];" % (k, 14 + i, i))
+        e("    *minpiv = evopf_factor(pt, lu, ipiv);")
+        e("    evopf_solve(lu, ipiv, r);")
+        e("    real n2 = RC(0.0);")
+        for k, (kind, j) in enumerate(self.unk):
+            if kind == "th":
+                e("    y[%d] += r[%d]; n2 = FMA(r[%d], r[%d], n2);" % (K.VA0 + j, k, k, k))
+            else:
+                e("    { const real dv_ = y[%d] * r[%d]; y[%d] += dv_; n2 = FMA(dv_, dv_, n2); }" % (K.VM0 + j, k, K.VM0 + j))
+        e("    return n2;")
+        e("}")
+        e("")
+        e("// Step 0 of the completion: scatter z, flat start (evopf.py:794-807).")
+        e("RPO_HD void evopf_init(const real* z, real* y) {")
+        for k in range(K.YDIM):
+            e_ = None
+        for g in range(K.NG):
+            e("    y[%d] = RC(0.0); y[%d] = RC(0.0);" % (K.PG0 + g, K.QG0 + g))
+        for k, g in enumerate(K.PV_):
+            e("    y[%d] = z[%d];" % (K.PG0 + int(g), int(K.PG_PV_ZIDX[k])))
+        for k, b in enumerate(K.SPV):
+            e("    y[%d] = z[%d];" % (K.VM0 + int(b), int(K.VM_SPV_ZIDX[k])))
+        for b in self.pq:
+            e("    y[%d] = %s;" % (K.VM0 + b, lit(K.VM_INIT[b])))
+        e("    y[%d] = %s;" % (K.VA0 + self.slack, lit(K.SLACK_VA[0])))
+        for b in self.pv + self.pq:
+            e("    y[%d] = %s;" % (K.VA0 + b, lit(K.VA_INIT[b])))
+        for g in range(K.NE):
+            e("    y[%d] = z[%d];" % (K.PE0 + g, int(K.PE_SPV_ZIDX[g])))
+        e("}")
+        e("")
+        e("// Step 2 of the completion: qg at all gens, pg at the slack (evopf.py:844-848), from flows at the final point.")
+        e("RPO_HD void evopf_tail(const real* x, real* y, const EvopfPt& pt) {")
+        for g, b in enumerate(self.spv):
+            e("    y[%d] = x[%d] + pt.Q[%d];" % (K.QG0 + g, 14 + b, b))
+        e("    y[%d] = (x[%d] - y[%d]) + pt.P[%d];" % (K.PG0 + 0, self.slack, K.PE0 + 0, self.slack))
+        e("}")
+        e("")
+
+    def gen_resid(self):
+        e = self.emit
+        e("// eq_resid (evopf.py:520-546) from a flows-evaluated point; returns max |resid|, optionally stores the 28 values.")
+        e("RPO_HD real evopf_eq_resid(const real* x, const real* y, const EvopfPt& pt, real* out) {")
+        e("    real m = RC(0.0), r_;")
+        for i in range(self.nb):
+            if i in self.spv:
+                g = self.spv.index(i)
+                e("    r_ = ((y[%d] + y[%d]) - x[%d]) - pt.P[%d];" % (K.PG0 + g, K.PE0 + g, i, i))
+            else:
+                e("    r_ = (-x[%d]) - pt.P[%d];" % (i, i))
+            e("    if (out) out[%d] = r_; m = FMAX(m, FABS(r_));" % i)
+        for i in range(self.nb):
+            if i in self.spv:
+                g = self.spv.index(i)
+                e("    r_ = (y[%d] - x[%d]) - pt.Q[%d];" % (K.QG0 + g, 14 + i, i))
+            else:
+                e("    r_ = (-x[%d]) - pt.Q[%d];" % (14 + i, i))
+            e("    if (out) out[%d] = r_; m = FMAX(m, FABS(r_));" % (14 + i))
+        e("    return m;")
+        e("}")
+        e("")
+        e("// Battery bounds in float64 then rounded, as Battery.ineq_resid does in numpy (evopf.py:109-116).")
+        e("RPO_HD void evopf_pe_bounds(const real* soc, real* pe_max, real* pe_min) {")
+        e("    for (int g = 0; g < 5; ++g) {")
+        e("        const double s = (double)soc[g];")
+        e("        const double hi = (1.0 / %r) * fmin(%r, %r - s);" % (K.ETA_IN, K.B_PMAX, K.B_HIGH))
+        e("        const double lo = %r * fmax(%r, %r - s);" % (K.ETA_OUT, K.B_PMIN, K.B_LOW))
+        e("        pe_max[g] = (real)hi; pe_min[g] = (real)lo;")
+        e("    }")
+        e("}")
+        e("")
+        e("// ineq_resid (evopf.py:548-563): 58 rows; returns max ineq_dist; optionally stores the residuals;")
+        e("// d[43] receives ineq_jac^T . 1[dist > 0] (evopf.py:590-594) when non-null.")
+        e("RPO_HD real evopf_ineq(const real* soc, const real* y, real* out, real* d) {")
+        e("    real pe_max[5], pe_min[5];")
+        e("    evopf_pe_bounds(soc, pe_max, pe_min);")
+        e("    real m = RC(0.0), hi_, lo_;")
+        rows = []
+
+        def pair(yidx, hi, lo, row_hi, row_lo):
+            e("    hi_ = y[%d] - %s; lo_ = %s - y[%d];" % (yidx, hi, lo, yidx))
+            e("    if (out) { out[%d] = hi_; out[%d] = lo_; }" % (row_hi, row_lo))
+            e("    m = FMAX(m, FMAX(hi_, lo_));")
+            e("    if (d) d[%d] = (hi_ > RC(0.0) ? RC(1.0) : RC(0.0)) - (lo_ > RC(0.0) ? RC(1.0) : RC(0.0));" % yidx)
+        ng, nb = K.NG, K.NBUS
+        for g in range(ng):
+            pair(K.PG0 + g, lit(K.PMAX_PU[g]), lit(K.PMIN_PU[g]), g, ng + g)
+        for g in range(ng):
+            pair(K.QG0 + g, lit(K.QMAX_PU[g]), lit(K.QMIN_PU[g]), 2 * ng + g, 3 * ng + g)
+        for i in range(nb):
+            pair(K.VM0 + i, lit(K.VMAX_PU[i]), lit(K.VMIN_PU[i]), 4 * ng + i, 4 * ng + nb + i)
+        for g in range(ng):
+            pair(K.PE0 + g, "pe_max[%d]" % g, "pe_min[%d]" % g, 4 * ng + 2 * nb + g, 5 * ng + 2 * nb + g)
+        e("    if (d) {")
+        for i in range(nb):
+            e("        d[%d] = RC(0.0);" % (K.VA0 + i))
+        e("    }")
+        e("    return m;")
+        e("}")
+        e("")
+
+    def L_rows(self):
+        return [("P", self.slack)] + [("Q", b) for b in self.spv]
+
+    def gen_transposed_rhs(self, fn_name, doc):
+        """rhs[c] = -(D gvec_w)[c] - sum_{rows in L} F[row, unk c] * tL[row];  tL: P_slack, Q_spv[0..4]."""
+        e = self.emit
+        e("// %s" % doc)
+        e("RPO_HD void %s(const real* y, const EvopfPt& pt, const real* gvec, const real* tL, real* rhs) {" % fn_name)
+        Lrows = self.L_rows()
+        for c, (kind, j) in enumerate(self.unk):
+            terms = []
+            for li, row in enumerate(Lrows):
+                f = self.F(row, (kind, j))
+                if f is not None:
+                    terms.append((f, "tL[%d]" % li))
+            if kind == "th":
+                init = "-gvec[%d]" % (K.VA0 + j)
+            else:
+                init = "-(y[%d] * gvec[%d])" % (K.VM0 + j, K.VM0 + j)
+            self.accum("rhs[%d]" % c, terms, init=init, negate=True)
+        e("}")
+        e("")
+
+    def gen_colsums(self):
+        """For columns V_j (j in spv) and th_slack: sum over all rows of F[row, col] * lam[row], lam = (lamP[14], lamQ[14])."""
+        e = self.emit
+        e("// cs[g] = sum_rows F[row, V_spv[g]] lam[row] (g = 0..4);  cs[5] = sum_rows F[row, th_slack] lam[row].")
+        e("RPO_HD void evopf_colsums(const EvopfPt& pt, const real* lamP, const real* lamQ, real* cs) {")
+        cols = [("V", b) for b in self.spv] + [("th", self.slack)]
+        for ci, col in enumerate(cols):
+            terms = []
+            for i in range(self.nb):
+                fp = self.F(("P", i), col)
+                if fp is not None:
+                    terms.append((fp, "lamP[%d]" % i))
+                fq = self.F(("Q", i), col)
+                if fq is not None:
+                    terms.append((fq, "lamQ[%d]" % i))
+            self.accum("cs[%d]" % ci, terms)
+        e("}")
+        e("")
+
+    def gen_backward(self):
+        e = self.emit
+        self.gen_transposed_rhs(
+            "evopf_rhs_t",
+            "Right-hand side of the transposed Newton solve shared by the GRG backward and the correction direction:"
+            " A~^T lam_N = -D g_w - F[L,w]^T t_L.")
+        self.gen_colsums()
+        e("// GRG backward (PFFunctionFn.backward evopf.py:857-910) with J recomputed at y.  g = dL/dy (43).")
+        e("// dz (14) and dx (28, may be null).")
+        e("RPO_HD real evopf_backward(const real* y, const real* g, real* dz, real* dx) {")
+        e("    EvopfPt pt; real lu[EVOPF_NLU], ipiv[EVOPF_NN], rhs[EVOPF_NN], tL[6], lamP[14], lamQ[14], cs[6];")
+        e("    evopf_eval_full(y, pt);")
+        e("    const real minpiv = evopf_factor(pt, lu, ipiv);")
+        e("    tL[0] = g[%d];" % (K.PG0 + 0))
+        for gi in range(K.NG):
+            e("    tL[%d] = g[%d];" % (1 + gi, K.QG0 + gi))
+        e("    evopf_rhs_t(y, pt, g, tL, rhs);")
+        e("    evopf_solve_t(lu, ipiv, rhs);")
+        e("    lamP[%d] = tL[0];" % self.slack)
+        for gi, b in enumerate(self.spv):
+            e("    lamQ[%d] = tL[%d];" % (b, 1 + gi))
+        for k, (kind, i) in enumerate(self.eqs):
+            e("    lam%s[%d] = rhs[%d];" % (kind, i, k))
+        e("    evopf_colsums(pt, lamP, lamQ, cs);")
+        for k, gidx in enumerate(K.PV_):
+            b = self.spv[int(gidx)]
+            e("    dz[%d] = g[%d] - lamP[%d];" % (int(K.PG_PV_ZIDX[k]), K.PG0 + int(gidx), b))
+        for gi, b in enumerate(self.spv):
+            e("    dz[%d] = FMA(cs[%d], RCP(y[%d]), g[%d]);" % (int(K.VM_SPV_ZIDX[gi]), gi, K.VM0 + b, K.VM0 + b))
+        for gi, b in enumerate(self.spv):
+            e("    dz[%d] = g[%d] + lamP[%d];" % (int(K.PE_SPV_ZIDX[gi]), K.PE0 + gi, b))
+        e("    if (dx) {")
+        for i in range(self.nb):
+            e("        dx[%d] = lamP[%d]; dx[%d] = lamQ[%d];" % (i, i, 14 + i, i))
+        e("    }")
+        e("    return minpiv;")
+        e("}")
+        e("")
+
+    def gen_direction(self):
+        e = self.emit
+        e("// Reduced correction direction = EVOPFEnv.ineq_partial_grad (evopf.py:596-612) in two-solve form")
+        e("// (SURVEY App. B.4) on the 22x22 Newton block (28x28 J_O is block triangular, SURVEY H3).")
+        e("// Also evaluates the loop test of grad_steps (rpo_ddpg.py:271-272): *eqmax = max|eq_resid|, *ineqmax = max ineq_dist.")
+        e("RPO_HD real evopf_direction(const real* x, const real* soc, const real* y, real* out, real* eqmax, real* ineqmax) {")
+        e("    EvopfPt pt; real lu[EVOPF_NLU], ipiv[EVOPF_NN], rhs[EVOPF_NN], d[43], tL[6], tP[14], tQ[14], cs[6], q[28];")
+        e("    evopf_eval_full(y, pt);")
+        e("    *eqmax = evopf_eq_resid(x, y, pt, (real*)0);")
+        e("    *ineqmax = evopf_ineq(soc, y, (real*)0, d);")
+        e("    const real minpiv = evopf_factor(pt, lu, ipiv);")
+        e("    tL[0] = d[%d];" % (K.PG0 + 0))
+        for gi in range(K.NG):
+            e("    tL[%d] = d[%d];" % (1 + gi, K.QG0 + gi))
+        e("    evopf_rhs_t(y, pt, d, tL, rhs);")
+        e("    evopf_solve_t(lu, ipiv, rhs);")
+        e("    tP[%d] = tL[0];" % self.slack)
+        for gi, b in enumerate(self.spv):
+            e("    tQ[%d] = tL[%d];" % (b, 1 + gi))
+        for k, (kind, i) in enumerate(self.eqs):
+            e("    t%s[%d] = rhs[%d];" % (kind, i, k))
+        e("    evopf_colsums(pt, tP, tQ, cs);")
+        # g_P
+        e("    real gpg[5], gpe[5], h[5], gvm[5];")
+        e("    gpg[0] = RC(0.0);")
+        for gidx in K.PV_:
+            gidx = int(gidx)
+            e("    gpg[%d] = d[%d] - tP[%d];" % (gidx, K.PG0 + gidx, self.spv[gidx]))
+        for gi, b in enumerate(self.spv):
+            e("    gpe[%d] = d[%d] + tP[%d];" % (gi, K.PE0 + gi, b))
+        for gi, b in enumerate(self.spv):
+            e("    { const real iv_ = RCP(y[%d]); gvm[%d] = FMA(cs[%d], iv_, d[%d]); h[%d] = gvm[%d] * iv_; }"
+              % (K.VM0 + b, gi, gi, K.VM0 + b, gi, gi))
+        e("    const real gva0 = cs[5];")
+        # q = J_P g_P (28 over equations), then rhs2 = -q_N
+        for i in range(self.nb):
+            for kind in ("P", "Q"):
+                terms = []
+                for gi, b in enumerate(self.spv):
+                    f = self.F((kind, i), ("V", b))
+                    if f is not None:
+                        terms.append((f, "h[%d]" % gi))
+                f = self.F((kind, i), ("th", self.slack))
+                if f is not None:
+                    terms.append((f, "gva0"))
+                init = None
+                if kind == "P" and i in self.spv:
+                    gi = self.spv.index(i)
+                    init = "(gpg[%d] - gpe[%d])" % (gi, gi)
+                tgt = "q[%d]" % (i if kind == "P" else 14 + i)
+                if init is None and not terms:
+                    e("    %s = RC(0.0);" % tgt)
+                elif init is None:
+                    self.accum(tgt, terms, negate=True)
+                else:
+                    self.accum(tgt, terms, init=init, negate=True)
+        for k, (kind, i) in enumerate(self.eqs):
+            e("    rhs[%d] = -q[%d];" % (k, i if kind == "P" else 14 + i))
+        e("    evopf_solve(lu, ipiv, rhs);")
+        # u_s = q_L + F[L, w] u~ ; out_O = -u
+        Lrows = self.L_rows()
+        Lout = [K.PG0 + 0] + [K.QG0 + gi for gi in range(K.NG)]
+        for li, row in enumerate(Lrows):
+            terms = []
+            for c, unk in enumerate(self.unk):
+                f = self.F(row, unk)
+                if f is not None:
+                    terms.append((f, "rhs[%d]" % c))
+            qidx = row[1] if row[0] == "P" else 14 + row[1]
+            e("    {")
+            e("    real u_;")
+            self.accum("u_", terms, init="q[%d]" % qidx)
+            e("    out[%d] = -u_;" % Lout[li])
+            e("    }")
+        for gidx in K.PV_:
+            e("    out[%d] = gpg[%d];" % (K.PG0 + int(gidx), int(gidx)))
+        for gi, b in enumerate(self.spv):
+            e("    out[%d] = gvm[%d];" % (K.VM0 + b, gi))
+        e("    out[%d] = gva0;" % (K.VA0 + self.slack))
+        for gi in range(K.NE):
+            e("    out[%d] = gpe[%d];" % (K.PE0 + gi, gi))
+        for c, (kind, j) in enumerate(self.unk):
+            if kind == "th":
+                e("    out[%d] = -rhs[%d];" % (K.VA0 + j, c))
+            else:
+                e("    out[%d] = -(y[%d] * rhs[%d]);" % (K.VM0 + j, K.VM0 + j, c))
+        e("    return minpiv;")
+        e("}")
+        e("")
+
+    def generate(self):
+        self.gen_header()
+        self.gen_eval()
+        self.gen_factor()
+        self.gen_newton()
+        self.gen_resid()
+        self.gen_backward()
+        self.gen_direction()
+        return "\n".join(self.out) + "\n"
+
+
+def main():
+    g = Gen()
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "rpo_b200", "csrc", "evopf_gen.cuh")
+    txt = g.generate()
+    with open(out, "w") as f:
+        f.write(txt)
+    print("order", g.order, "nnzY", g.nnz, "nL", g.nL, "nU", g.nU, "lu_ops", g.lu_ops, "lines", txt.count("\n"))
+
+
+if __name__ == "__main__":
+    main()
