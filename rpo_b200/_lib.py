@@ -10,7 +10,8 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librpo_b200.so")
+# RPO_B200_LIB overrides the path for kernel-variant experiments (tools/variant_sweep.py); the product uses the in-tree build.
+LIB_PATH = os.environ.get("RPO_B200_LIB") or os.path.join(_HERE, "librpo_b200.so")
 
 RPO_OK = 0
 

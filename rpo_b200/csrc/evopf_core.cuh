@@ -50,10 +50,10 @@ RPO_HD int evopf_complete(const real* x, const real* z, real* y, real tol, int m
 //   dir = ineq_partial_grad(state, y);  step = lr*dir + momentum*prev;  y -= step;  prev = step.
 // Returns whether this instance fails the loop test *before* the step (|eq_resid| or ineq_dist above eps).
 template <bool MOMENTUM>
-RPO_HD bool evopf_correct_step(const real* x, const real* soc, real* y, real* prev, real lr, real momentum,
-                               real corr_eps, real* minpiv) {
+RPO_HD bool evopf_correct_step(const real* x, const real* pe_max, const real* pe_min, real* y, real* prev, real lr,
+                               real momentum, real corr_eps, real* minpiv) {
     real dir[43], eqmax, ineqmax;
-    *minpiv = evopf_direction(x, soc, y, dir, &eqmax, &ineqmax);
+    *minpiv = evopf_direction(x, pe_max, pe_min, y, dir, &eqmax, &ineqmax);
     for (int i = 0; i < 43; ++i) {
         real s = lr * dir[i];
         if (MOMENTUM) {

@@ -24,18 +24,59 @@ typedef RPO_REAL real;
 
 #define RC(x) ((real)(x))
 
+// RPO_ALIGN(n): markers the generator drops every 32 statements of the big straight-line functions.  On the device,
+// when RPO_ALIGN_EVERY > 0, every RPO_ALIGN_EVERY-th marker is a block barrier that keeps the warps of a CTA within
+// one instruction-cache window of each other (the kernels are instruction-fetch bound).
+#ifndef RPO_ALIGN_EVERY
+#define RPO_ALIGN_EVERY 0
+#endif
+#if defined(__CUDA_ARCH__) && RPO_ALIGN_EVERY > 0
+#define RPO_ALIGN(n) do { if ((n) % RPO_ALIGN_EVERY == 0) __syncthreads(); } while (0)
+#else
+#define RPO_ALIGN(n) do { } while (0)
+#endif
+
+// ---- branch-free single-precision sincos -------------------------------------------------------------
+// Cody-Waite 3-term reduction by pi/2 (exact for |x| up to ~1e5 rad; voltage angles live in [-pi, pi]) and the
+// Cephes minimax polynomials on [-pi/4, pi/4] (max error ~1 ulp).  Same code on host (hostsim) and device; it
+// replaces CUDA's sincosf, whose inlined Payne-Hanek slow path made up ~1/3 of the kernel's instructions.
+RPO_HD void rpo_sincosf(float x, float* sp, float* cp) {
+    const float kf = rintf(x * 0.63661977236758134f);
+    float r = fmaf(kf, -0x1.921fb6p+0f, x);          // pi/2 = C1 + C2 + C3, C1 = float(pi/2); the FMA keeps k*C exact
+    r = fmaf(kf, 0x1.777a5cp-25f, r);
+    r = fmaf(kf, 0x1.ee59dap-50f, r);
+    const float r2 = r * r;
+    float ps = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+    ps = fmaf(ps, r2, -1.6666654611e-1f);
+    const float s = fmaf(r * r2, ps, r);
+    float pc = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    pc = fmaf(pc, r2, 4.166664568298827e-2f);
+    pc = fmaf(pc, r2, -0.5f);
+    const float c = fmaf(pc, r2, 1.0f);
+    const int q = (int)kf;
+    const float ss = (q & 1) ? c : s;
+    const float cc = (q & 1) ? s : c;
+    *sp = (q & 2) ? -ss : ss;
+    *cp = ((q + 1) & 2) ? -cc : cc;
+}
+
 #if defined(__CUDA_ARCH__)
 // device, float only (the CUDA build is always float)
+RPO_D float rpo_rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 #define FMA(a, b, c) __fmaf_rn((a), (b), (c))
-#define SINCOS(x, s, c) sincosf((x), (s), (c))
-#define RCP(x) __frcp_rn(x)
+#define SINCOS(x, s, c) rpo_sincosf((x), (s), (c))
+#define RCP(x) rpo_rcp_approx(x)
 #define FMIN(a, b) fminf((a), (b))
 #define FMAX(a, b) fmaxf((a), (b))
 #define FABS(a) fabsf(a)
 #else
 static inline float rpo_fma_(float a, float b, float c) { return fmaf(a, b, c); }
 static inline double rpo_fma_(double a, double b, double c) { return fma(a, b, c); }
-static inline void rpo_sincos_(float x, float* s, float* c) { *s = sinf(x); *c = cosf(x); }
+static inline void rpo_sincos_(float x, float* s, float* c) { rpo_sincosf(x, s, c); }
 static inline void rpo_sincos_(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
 #define FMA(a, b, c) rpo_fma_((real)(a), (real)(b), (real)(c))
 #define SINCOS(x, s, c) rpo_sincos_((x), (s), (c))

@@ -1,0 +1,65 @@
+"""Host-buffer entry point of the projection path: the call a user of the reference makes with CPU data.
+
+The reference's callers hold numpy / CPU-torch batches (replay samples, rollout states — rpo_ddpg.py:93,165-174)
+and receive CPU arrays back (rpo_ddpg.py:108-109).  `HostProjector` takes pinned host buffers, streams them to the
+GPU in chunks on several CUDA streams (H2D copy, kernels and D2H copy of different chunks overlap), and writes the
+results into pinned host buffers.  Used by bench.py for the end-to-end (`e2e`) number.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+
+
+class HostProjector(object):
+    def __init__(self, device, chunk: int = 1 << 16, n_streams: int = 4, corr_lr: float = 1e-4, momentum: float = 0.0,
+                 corr_eps: float = 1e-5, n_steps: int = 10, tol: float = 1e-5, max_iters: int = 50):
+        self.device = torch.device(device)
+        self.chunk = int(chunk)
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(n_streams)]
+        self.p = dict(lr=corr_lr, momentum=momentum, corr_eps=corr_eps, n_steps=n_steps, tol=tol, max_iters=max_iters)
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        self.launches = 0
+
+    @staticmethod
+    def pinned(*shape, dtype=torch.float32):
+        return torch.empty(*shape, dtype=dtype, pin_memory=True)
+
+    def project_backward(self, state: torch.Tensor, z: torch.Tensor, dl_dy: Optional[torch.Tensor],
+                         y_corr_out: torch.Tensor, dl_dz_out: Optional[torch.Tensor]):
+        """state (B,57|33), z (B,14), dl_dy (B,43) pinned CPU float32 -> y_corr_out (B,43), dl_dz_out (B,14) pinned CPU.
+        Completion + correction (+ GRG backward of the completion when dl_dy is given).  Blocks until results landed."""
+        B = z.shape[0]
+        p = self.p
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            s.wait_stream(cur)
+        self.h2d_bytes = self.d2h_bytes = self.launches = 0
+        for i, b0 in enumerate(range(0, B, self.chunk)):
+            b1 = min(B, b0 + self.chunk)
+            s = self.streams[i % len(self.streams)]
+            with torch.cuda.stream(s):
+                d_state = state[b0:b1].to(self.device, non_blocking=True)
+                d_z = z[b0:b1].to(self.device, non_blocking=True)
+                self.h2d_bytes += (state[b0:b1].numel() + z[b0:b1].numel()) * 4
+                yc, y, _, _ = ops.evopf_project(d_state, d_z, p["lr"], p["momentum"], p["corr_eps"], p["n_steps"],
+                                                tol=p["tol"], max_iters=p["max_iters"], want_y=dl_dy is not None,
+                                                want_flags=False)
+                self.launches += 1
+                y_corr_out[b0:b1].copy_(yc, non_blocking=True)
+                self.d2h_bytes += yc.numel() * 4
+                if dl_dy is not None:
+                    d_g = dl_dy[b0:b1].to(self.device, non_blocking=True)
+                    self.h2d_bytes += d_g.numel() * 4
+                    dz, _ = ops.evopf_complete_bwd(y, d_g, need_dx=False)
+                    self.launches += 1
+                    dl_dz_out[b0:b1].copy_(dz, non_blocking=True)
+                    self.d2h_bytes += dz.numel() * 4
+        for s in self.streams:
+            cur.wait_stream(s)
+        cur.synchronize()
+        return y_corr_out, dl_dz_out

@@ -20,21 +20,24 @@ void hs_evopf_backward(const real* y, const real* g, real* dz, real* dx, int B) 
 }
 
 void hs_evopf_direction(const real* state, int ld, const real* y, real* out, real* eqmax, real* ineqmax, int B) {
-    for (int b = 0; b < B; ++b)
-        evopf_direction(state + (long)b * ld, state + (long)b * ld + 28, y + (long)b * 43, out + (long)b * 43,
-                        eqmax + b, ineqmax + b);
+    for (int b = 0; b < B; ++b) {
+        real pe_max[5], pe_min[5];
+        evopf_pe_bounds(state + (long)b * ld + 28, pe_max, pe_min);
+        evopf_direction(state + (long)b * ld, pe_max, pe_min, y + (long)b * 43, out + (long)b * 43, eqmax + b, ineqmax + b);
+    }
 }
 
 // flags[k] |= 1 if any instance fails the loop test before step k (k = 0..n_steps-1)
 void hs_evopf_correct(const real* state, int ld, real* y, int B, real lr, real momentum, real corr_eps, int n_steps,
                       int* flags) {
     for (int b = 0; b < B; ++b) {
-        real prev[43];
+        real prev[43], pe_max[5], pe_min[5];
         for (int i = 0; i < 43; ++i) prev[i] = 0;
+        evopf_pe_bounds(state + (long)b * ld + 28, pe_max, pe_min);
         for (int k = 0; k < n_steps; ++k) {
             real mp;
-            bool unsat = evopf_correct_step<true>(state + (long)b * ld, state + (long)b * ld + 28, y + (long)b * 43,
-                                                  prev, lr, momentum, corr_eps, &mp);
+            bool unsat = evopf_correct_step<true>(state + (long)b * ld, pe_max, pe_min, y + (long)b * 43, prev, lr, momentum,
+                                                  corr_eps, &mp);
             if (unsat && flags) flags[k] = 1;
         }
     }
@@ -45,7 +48,9 @@ void hs_evopf_resid(const real* state, int ld, const real* y, real* eq, real* in
         EvopfPt pt;
         evopf_eval_flows(y + (long)b * 43, pt);
         evopf_eq_resid(state + (long)b * ld, y + (long)b * 43, pt, eq + (long)b * 28);
-        evopf_ineq(state + (long)b * ld + 28, y + (long)b * 43, ineq + (long)b * 58, (real*)0);
+        real pe_max[5], pe_min[5];
+        evopf_pe_bounds(state + (long)b * ld + 28, pe_max, pe_min);
+        evopf_ineq(pe_max, pe_min, y + (long)b * 43, ineq + (long)b * 58, (real*)0);
     }
 }
 

@@ -62,6 +62,8 @@ class Gen(object):
         assert self.n == 22
         self.symbolic()
         self.out = []
+        self.align_on = False
+        self.align_cnt = 0
 
     # ---------------------------------------------------------------- symbolic work
     def min_degree_order(self):
@@ -121,6 +123,14 @@ class Gen(object):
 
     def emit(self, s=""):
         self.out.append(s)
+        if self.align_on and s.startswith("    ") and not s.startswith("     ") and s.rstrip().endswith(";"):
+            self.align_cnt += 1
+            if self.align_cnt % 32 == 0:
+                self.out.append("    RPO_ALIGN(%d);" % (self.align_cnt // 32))
+
+    def align(self, on):
+        """Enable/disable instruction-fetch alignment markers (see RPO_ALIGN in rpo_math.cuh)."""
+        self.align_on = on
 
     def accum(self, target, terms, init=None, negate=False):
         """Emit target = init (+|-) sum(a*b) as an FMA chain.  terms: list of (exprA, exprB)."""
@@ -165,6 +175,7 @@ class Gen(object):
             name = "evopf_eval_full" if full else "evopf_eval_flows"
             e("// y -> point quantities (%s)" % ("flows + Jacobian terms" if full else "flows only"))
             e("RPO_HD void %s(const real* y, EvopfPt& pt) {" % name)
+            self.align(bool(full))
             for i in range(self.nb):
                 e("    { real s_, c_; SINCOS(y[%d], &s_, &c_); pt.vr[%d] = y[%d] * c_; pt.vi[%d] = y[%d] * s_; }"
                   % (K.VA0 + i, i, K.VM0 + i, i, K.VM0 + i))
@@ -215,6 +226,7 @@ class Gen(object):
                     e("    pt.Hd[%d] = t2d_ - pt.Q[%d]; pt.Nd[%d] = t1d_ + pt.P[%d];" % (i, i, i, i))
                     e("    pt.Md[%d] = pt.P[%d] - t1d_; pt.Ld[%d] = t2d_ + pt.Q[%d];" % (i, i, i, i))
                 e("    }")
+            self.align(False)
             e("}")
             e("")
 
@@ -224,6 +236,7 @@ class Gen(object):
         e("// In-place sparse LU (no pivoting, static order) of the scaled Newton matrix A~ = F[N rows, w cols].")
         e("// lu[] holds the strict-lower multipliers and U; ipiv[] the pivot reciprocals.  Returns min |pivot|.")
         e("RPO_HD real evopf_factor(const EvopfPt& pt, real* lu, real* ipiv) {")
+        self.align(True)
         zero = set()
         for (r, c), idx in sorted(self.luidx.items(), key=lambda kv: kv[1]):
             if self.orig[r][c]:
@@ -250,12 +263,14 @@ class Gen(object):
                     else:
                         e("    lu[%d] = FMA(-lu[%d], lu[%d], lu[%d]);" % (ij, ik, kj, ij))
         assert not zero
+        self.align(False)
         e("    return minpiv;")
         e("}")
         e("")
         # solves
         e("// x <- A~^{-1} x  (x indexed by elimination position: in = equations, out = unknowns)")
         e("RPO_HD void evopf_solve(const real* lu, const real* ipiv, real* x) {")
+        self.align(True)
         for k in range(n):
             for i in range(k + 1, n):
                 if self.pat[i][k]:
@@ -265,10 +280,12 @@ class Gen(object):
                 if self.pat[k][j]:
                     e("    x[%d] = FMA(-lu[%d], x[%d], x[%d]);" % (k, self.luidx[(k, j)], j, k))
             e("    x[%d] *= ipiv[%d];" % (k, k))
+        self.align(False)
         e("}")
         e("")
         e("// x <- A~^{-T} x  (in = unknown positions, out = equation positions)")
         e("RPO_HD void evopf_solve_t(const real* lu, const real* ipiv, real* x) {")
+        self.align(True)
         # U^T w = b : forward over columns of U
         for k in range(n):
             for j in range(k):
@@ -280,6 +297,7 @@ class Gen(object):
             for i in range(k + 1, n):
                 if self.pat[i][k]:
                     e("    x[%d] = FMA(-lu[%d], x[%d], x[%d]);" % (k, self.luidx[(i, k)], i, k))
+        self.align(False)
         e("}")
         e("")
 
@@ -376,10 +394,8 @@ class Gen(object):
         e("}")
         e("")
         e("// ineq_resid (evopf.py:548-563): 58 rows; returns max ineq_dist; optionally stores the residuals;")
-        e("// d[43] receives ineq_jac^T . 1[dist > 0] (evopf.py:590-594) when non-null.")
-        e("RPO_HD real evopf_ineq(const real* soc, const real* y, real* out, real* d) {")
-        e("    real pe_max[5], pe_min[5];")
-        e("    evopf_pe_bounds(soc, pe_max, pe_min);")
+        e("// d[43] receives ineq_jac^T . 1[dist > 0] (evopf.py:590-594) when non-null.  pe_max/pe_min from evopf_pe_bounds.")
+        e("RPO_HD real evopf_ineq(const real* pe_max, const real* pe_min, const real* y, real* out, real* d) {")
         e("    real m = RC(0.0), hi_, lo_;")
         rows = []
 
@@ -491,11 +507,11 @@ class Gen(object):
         e("// Reduced correction direction = EVOPFEnv.ineq_partial_grad (evopf.py:596-612) in two-solve form")
         e("// (SURVEY App. B.4) on the 22x22 Newton block (28x28 J_O is block triangular, SURVEY H3).")
         e("// Also evaluates the loop test of grad_steps (rpo_ddpg.py:271-272): *eqmax = max|eq_resid|, *ineqmax = max ineq_dist.")
-        e("RPO_HD real evopf_direction(const real* x, const real* soc, const real* y, real* out, real* eqmax, real* ineqmax) {")
+        e("RPO_HD real evopf_direction(const real* x, const real* pe_max, const real* pe_min, const real* y, real* out, real* eqmax, real* ineqmax) {")
         e("    EvopfPt pt; real lu[EVOPF_NLU], ipiv[EVOPF_NN], rhs[EVOPF_NN], d[43], tL[6], tP[14], tQ[14], cs[6], q[28];")
         e("    evopf_eval_full(y, pt);")
         e("    *eqmax = evopf_eq_resid(x, y, pt, (real*)0);")
-        e("    *ineqmax = evopf_ineq(soc, y, (real*)0, d);")
+        e("    *ineqmax = evopf_ineq(pe_max, pe_min, y, (real*)0, d);")
         e("    const real minpiv = evopf_factor(pt, lu, ipiv);")
         e("    tL[0] = d[%d];" % (K.PG0 + 0))
         for gi in range(K.NG):

@@ -3,7 +3,7 @@ sys.path.insert(0, '.')
 import torch
 from rpo_b200 import ops, synth, _lib
 print('arch', _lib.load().rpo_build_arch(), torch.cuda.get_device_name(0))
-B = 1<<18
+B = 1<<20
 st = synth.evopf_states(B, seed=0).cuda(); z = synth.evopf_partial_actions(st, seed=1).cuda(); g = synth.upstream_grad(B, 43).cuda()
 def timeit(f, n=5):
     for _ in range(2): f()
