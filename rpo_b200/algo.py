@@ -1,0 +1,87 @@
+"""Drivers of the projection: process_action / grad_steps with the reference's signatures
+(rpo/algo/rpo_ddpg.py:72-77,266-305; rpo/algo/rpo_sac.py:76-81,280-319).
+
+`grad_steps` runs the whole post-correction loop in ONE kernel launch.  The reference decides after every step,
+on the host, whether the *global* max of |eq_resid| / ineq_dist over the batch still exceeds corr_eps (two
+device->host syncs per step).  The kernel instead records, per step, whether any instance failed that test; the
+host reads the K flags once and, in the rare case that the reference would have stopped early (k < K), re-runs the
+kernel with n_steps = k from the original action — same trajectory, so the result equals the reference's loop.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+
+
+def reference_step_count(flags: torch.Tensor, limit: int) -> int:
+    """Steps the reference's while-loop takes: `step == 0 or unsat` and `step < limit` (rpo_ddpg.py:271-272)."""
+    if limit <= 0:
+        return 0
+    fl = flags[:limit].tolist()          # one small device->host read
+    for k in range(1, limit):
+        if fl[k] == 0:
+            return k
+    return limit
+
+
+def grad_steps_env(env, state, action, lr: float, momentum: float, corr_eps: float, limit: int,
+                   exact: bool = True) -> Tuple[torch.Tensor, int]:
+    """Post-correction loop for corr_mode == 0 on any rpo_b200 env.  Returns (action, steps)."""
+    if limit <= 0:
+        return action, 0
+    out, flags = env.correct(state, action.detach(), lr, momentum, corr_eps, limit)
+    if not exact:
+        return out, limit
+    k = reference_step_count(flags, limit)
+    if k < limit:
+        out, _ = env.correct(state, action.detach(), lr, momentum, corr_eps, k)
+    return out, k
+
+
+class RPOProjectionMixin(object):
+    """Mix into (or patch onto) rpo.algo.RPODDPG / RPOSAC: same attribute names, same return conventions."""
+
+    exact_loop_exit = True
+
+    def grad_steps(self, state, action, train=True):
+        if getattr(self, "corr_mode", 0) != 0:
+            raise NotImplementedError("corr_mode != 0 is not on the B200 path (unused by every reference script)")
+        if train:
+            a, _ = grad_steps_env(self.env, state, action, self.corr_lr, self.corr_momentum, self.corr_eps,
+                                  self.max_steps, self.exact_loop_exit)
+            return a
+        with torch.no_grad():
+            return grad_steps_env(self.env, state, action, self.eval_lr, self.corr_momentum, self.corr_eps,
+                                  self.eval_steps, self.exact_loop_exit)
+
+    def process_action(self, state, action_partial, train=True):
+        needs_grad = torch.is_grad_enabled() and (action_partial.requires_grad or state.requires_grad)
+        if needs_grad or getattr(self, "corr_mode", 0) != 0:
+            action = self.env.complete_partial(state, action_partial)
+            return self.grad_steps(state, action, train=train)
+        # no-grad call sites (rpo_ddpg.py:100,106,233,330): fused completion + correction, one launch
+        lr, limit = (self.corr_lr, self.max_steps) if train else (self.eval_lr, self.eval_steps)
+        yc, y, flags = self.env.project(state, action_partial, lr, self.corr_momentum, self.corr_eps, limit)
+        k = limit
+        if self.exact_loop_exit:
+            k = reference_step_count(flags, limit)
+            if k < limit:
+                yc, _ = self.env.correct(state, y, lr, self.corr_momentum, self.corr_eps, k)
+        return yc if train else (yc, k)
+
+
+def install(rpo_module=None, register_envs: bool = True):
+    """Route the reference's own RPODDPG / RPOSAC through the B200 path: patches
+    process_action / grad_steps on the two classes and re-registers the gym ids to rpo_b200.env classes."""
+    if rpo_module is None:
+        import rpo as rpo_module           # the reference package
+    import rpo.algo as ralgo
+    for cls in (ralgo.RPODDPG, ralgo.RPOSAC):
+        cls.process_action = RPOProjectionMixin.process_action
+        cls.grad_steps = RPOProjectionMixin.grad_steps
+        cls.exact_loop_exit = True
+    if register_envs:
+        from .env import register_all
+        register_all(force=True)
+    return rpo_module

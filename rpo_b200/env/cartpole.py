@@ -1,0 +1,146 @@
+"""CartSafe-v0 drop-in: the API of rpo.env.CartSafeEnv (rpo/env/classic_control/cartpole.py) over the CUDA kernels."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from .. import ops
+from .spaces import Box
+
+
+class _CompleteFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, partial_idx):
+        ctx.partial_idx = partial_idx
+        return ops.cart_complete_fwd(z, partial_idx)
+
+    @staticmethod
+    def backward(ctx, dl_da):
+        return ops.cart_complete_bwd(dl_da.contiguous(), ctx.partial_idx), None
+
+
+class CartSafeEnv(object):
+    metadata = {"render_modes": ["human", "rgb_array"], "render_fps": 50}
+
+    def __init__(self, device=None, partial_idx=None):
+        self.gravity, self.masscart, self.masspole = 9.8, 1.0, 0.1
+        self.total_mass = self.masspole + self.masscart
+        self.length = 0.5
+        self.polemass_length = self.masspole * self.length
+        self.tau = 0.02
+        self.mu_c, self.mu_p = 0.1, 0.01
+        self.delta = np.array([np.pi / 3, -np.pi / 6])
+        self.theta_threshold_radians = 12 * 2 * math.pi / 360
+        self.x_threshold = 2.4
+        fmax = np.finfo(np.float32).max
+        high = np.array([self.x_threshold * 2, fmax, fmax, self.theta_threshold_radians * 2, fmax, fmax], dtype=np.float32)
+        self.observation_space = Box(-high, high, dtype=np.float32)
+        self.action_space = Box(np.array([-10, -10]).astype(np.float32), np.array([10, 10]).astype(np.float32))
+        self.state_dim, self.action_dim, self.eq_num, self.ineq_num = 6, 2, 1, 6
+        self.seed()
+        self.state = None
+        # cartpole.py:117: the policy-controlled force is drawn at random at construction (global numpy RNG)
+        if partial_idx is None:
+            self.partial_actions = np.random.choice(self.action_dim, self.action_dim - self.eq_num, replace=False)
+        else:
+            self.partial_actions = np.array([int(partial_idx)])
+        self.other_actions = np.setdiff1d(np.arange(self.action_dim), self.partial_actions)
+        self.steps_beyond_done = None
+        self.device = torch.device(device) if device is not None else torch.device("cuda")
+        self.volatile = False
+        self.update = None
+        self.action = None
+        self.last_state = None
+
+    @property
+    def _p(self):
+        return int(self.partial_actions[0])
+
+    def seed(self, seed=None):
+        self.np_random = np.random.RandomState(seed)
+        return [seed]
+
+    def _t(self, a):
+        t = a.to(device=self.device, dtype=torch.float32) if isinstance(a, torch.Tensor) else \
+            torch.as_tensor(np.asarray(a), dtype=torch.float32, device=self.device)
+        return t.view(1, -1) if t.dim() == 1 else t
+
+    # ---- hard-constraint protocol (cartpole.py:369-408) -------------------------------------------------
+    def complete_partial(self, state, action_partial):
+        z = action_partial.view(-1, 1) if action_partial.dim() == 1 else action_partial
+        return _CompleteFn.apply(z, self._p)
+
+    def eq_resid(self, state, action):
+        return ops.cart_resid(action, want_ineq=False)[0]
+
+    def ineq_resid(self, state, action):
+        return ops.cart_resid(action, want_eq=False)[1]
+
+    def eq_dist(self, state, action):
+        return torch.abs(self.eq_resid(state, action))
+
+    def ineq_dist(self, state, action):
+        return torch.clamp(self.ineq_resid(state, action), 0)
+
+    def ineq_partial_grad(self, state, action, eps=0):
+        return ops.cart_direction(action, self._p)
+
+    def ineq_dist_np(self, state, action):
+        return self.ineq_dist(None, self._t(action)).cpu().numpy()[0]
+
+    def eq_resid_np(self, state, action):
+        return self.eq_resid(None, self._t(action)).cpu().numpy()[0]
+
+    def correct(self, state, action, lr, momentum, corr_eps, n_steps):
+        return ops.cart_correct(action, self._p, lr, momentum, corr_eps, n_steps)
+
+    def project(self, state, action_partial, lr, momentum, corr_eps, n_steps):
+        z = action_partial.view(-1, 1) if action_partial.dim() == 1 else action_partial
+        ac, a, flags = ops.cart_project(z, self._p, lr, momentum, corr_eps, n_steps, want_a=True)
+        return ac, a, flags
+
+    @property
+    def box_constraint(self):
+        return self.action_space.low, self.action_space.high
+
+    @property
+    def box_constraint_partial(self):
+        return self.action_space.low[self.partial_actions], self.action_space.high[self.partial_actions]
+
+    # ---- gym API (cartpole.py:166-239) ---------------------------------------------------------------------
+    def reset(self):
+        self.state = self.np_random.uniform(low=-0.05, high=0.05, size=(6,))
+        self.action = None
+        self.last_state = None
+        self.steps_beyond_done = None
+        return np.array(self.state)
+
+    def step(self, action):
+        action = np.asarray(action, dtype=np.float32)
+        ns, done, eqv, iqv = ops.cart_step(self._t(self.state), self._t(action))
+        self.last_state = np.array(self.state)
+        self.action = action.copy()
+        self.state = tuple(ns[0].double().cpu().numpy())
+        done = bool(done[0].item())
+        if not done:
+            reward = 1.0
+        elif self.steps_beyond_done is None:
+            self.steps_beyond_done = 0
+            reward = 1.0
+        else:
+            self.steps_beyond_done += 1
+            reward = 0.0
+        info = {"ineq_viol": iqv.cpu().numpy()[0], "eq_viol": eqv.cpu().numpy()[0]}
+        return np.array(self.state), reward, done, info
+
+    def step_batch(self, state, action):
+        """(B,6), (B,2) device tensors -> next_state, done(int32), eq_viol, ineq_viol."""
+        return ops.cart_step(state, action)
+
+    def render(self, mode="human"):
+        raise NotImplementedError("rendering is outside the hot path")
+
+    def close(self):
+        pass

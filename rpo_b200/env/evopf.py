@@ -1,0 +1,241 @@
+"""EVOPF-v0 drop-in: the API of rpo.env.EVOPFEnv (rpo/env/electrical_grid/evopf.py:190-783) over the CUDA kernels.
+
+Attributes and method signatures follow the reference so that rpo.algo.RPODDPG / RPOSAC (and anything else that
+speaks the hard-constraint protocol) can use this class unchanged; every protocol method is one
+kernel launch through the C ABI (rpo_b200.ops).  Tensors live on ``self.device`` (CUDA): there is no CPU path.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from .. import evopf_constants as K
+from .. import ops
+from ..case14 import case14
+from .loaders import DemandLoader, PriceLoader
+from .spaces import Box
+
+
+class _CompleteFn(torch.autograd.Function):
+    """PFFunctionFn (evopf.py:787-910).  Saves only y (B,43): the backward kernel rebuilds the Jacobian from it,
+    where the reference saves a (B,28,43) Jacobian and a (B,22,22) inverse (evopf.py:851-853)."""
+
+    @staticmethod
+    def forward(ctx, x, z, tol, max_iters):
+        y = ops.evopf_complete_fwd(x, z, tol=tol, max_iters=max_iters)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dl_dy):
+        (y,) = ctx.saved_tensors
+        dz, dx = ops.evopf_complete_bwd(y, dl_dy.contiguous(), need_dx=ctx.needs_input_grad[0])
+        return dx, dz, None, None
+
+
+class Battery(object):
+    """Host-side bookkeeping of the 5 batteries (evopf.py:23-149); the arithmetic of step / ineq_resid runs in the kernels."""
+
+    def __init__(self, p_data, num, genbase, low=K.B_LOW, high=K.B_HIGH, p_min=K.B_PMIN, p_max=K.B_PMAX,
+                 eta_in=K.ETA_IN, eta_out=K.ETA_OUT, init_strategy="empty", residual=1.0):
+        self.p_data, self.num, self.genbase = p_data, num, genbase
+        self.low, self.high, self.p_min, self.p_max = low, high, p_min, p_max
+        self.eta_in, self.eta_out = eta_in, eta_out
+        self.init_strategy, self.residual = init_strategy, residual
+        self.state = None
+
+    def reset(self):                                            # evopf.py:54-72
+        state_p, _ = self.p_data.reset()
+        state_p = state_p / self.genbase
+        if self.init_strategy == "random":
+            state_b = np.random.dirichlet(np.ones(self.num)) * self.residual + self.low
+        elif self.init_strategy == "empty":
+            state_b = np.ones(self.num) * (self.low + 0.1)
+        elif self.init_strategy == "full":
+            state_b = np.ones(self.num) * self.high
+        else:
+            raise NotImplementedError
+        self.state = np.concatenate([state_b, state_p])
+        return self.state.copy()
+
+    def update_bound(self, soc: np.ndarray):                    # evopf.py:127-143 (float64 numpy)
+        soc = np.asarray(soc, dtype=np.float64)                 # the reference subtracts from float64 arrays (:135-138)
+        new_p_max = (1.0 / self.eta_in) * np.minimum(self.p_max, self.high - soc)
+        new_p_min = self.eta_out * np.maximum(self.p_min, self.low - soc)
+        return new_p_max, new_p_min
+
+
+class EVOPFEnv(object):
+    metadata = {"render.modes": ["human", "rgb_array"], "video.frames_per_second": 50}
+
+    def __init__(self, device=None, demand_curve=None, price_curve=None, data_dir=None):
+        self._device = torch.device(device) if device is not None else torch.device("cuda")
+        ppc = case14()
+        self.ppc = ppc
+        data_dir = data_dir or os.environ.get("RPO_EVOPF_DATA_DIR")
+        dp = os.path.join(data_dir, "demand.pickle") if data_dir else None
+        pp = os.path.join(data_dir, "price.pickle") if data_dir else None
+        self.data = DemandLoader(ppc=ppc, rho=0.5, q_rand=True, T=24, min_pf=0.9, max_pf=1.0, regularized=True,
+                                 curve=demand_curve, pickle_path=dp)                     # evopf.py:212
+        self.nahead = 24
+        self.p_data = PriceLoader(T=24, ahead=self.nahead, regularized=True, reg_bias=0.1, reg_sigma=0.05,
+                                  curve=price_curve, pickle_path=pp)                      # evopf.py:216
+        self.nbus, self.ng, self.ne = K.NBUS, K.NG, K.NE
+        self.genbase, self.baseMVA = K.GENBASE.copy(), K.BASE_MVA
+        self.slack, self.pv, self.spv, self.pq = K.SLACK.copy(), K.PV.copy(), K.SPV.copy(), K.PQ.copy()
+        self.slack_, self.pv_, self.spv_ = K.SLACK_.copy(), K.PV_.copy(), K.SPV_.copy()
+        self.nslack, self.npv = K.NSLACK, K.NPV
+        self.evs = Battery(self.p_data, num=self.ne, genbase=self.baseMVA, init_strategy="empty")
+        self.we, self.wg = K.WE, K.WG
+        self._xdim, self._ydim = K.XDIM, K.YDIM
+        self._neq, self._nineq, self._nknowns = 2 * K.NBUS, 4 * K.NG + 2 * K.NBUS, K.NSLACK
+        self.pg_start_yidx, self.qg_start_yidx, self.vm_start_yidx = K.PG0, K.QG0, K.VM0
+        self.va_start_yidx, self.pe_start_yidx = K.VA0, K.PE0
+        self._partial_vars, self._other_vars = K.PARTIAL_VARS.copy(), K.OTHER_VARS.copy()
+        self._partial_actions, self._other_actions = K.PARTIAL_ACTIONS.copy(), K.OTHER_ACTIONS.copy()
+        self.pg_pv_zidx, self.vm_spv_zidx = K.PG_PV_ZIDX.copy(), K.VM_SPV_ZIDX.copy()
+        self.pe_pv_zidx, self.pe_spv_zidx = K.PE_PV_ZIDX.copy(), K.PE_SPV_ZIDX.copy()
+        high = np.array([10.0] * 14 + [10.0] * 14 + [self.evs.high] * 5 + [240.0] * 24)
+        low = np.array([-10.0] * 14 + [-10.0] * 14 + [self.evs.low] * 5 + [0.0] * 24)
+        self.action_space = Box(low=K.ACTION_LOW.copy(), high=K.ACTION_HIGH.copy(), dtype=np.float32)
+        self.observation_space = Box(low=low, high=high, dtype=np.float32)
+        self.state_dim, self.action_dim = K.STATE_DIM, K.YDIM
+        self.eq_num, self.ineq_num = K.EQ_NUM, K.INEQ_NUM
+        self.newton_tol, self.newton_max_iters = K.NEWTON_TOL, K.NEWTON_MAX_ITERS         # evopf.py:786
+        self.state = None
+        self.action = None
+        self.volatile = True
+
+    # ---- properties of the reference (evopf.py:457-499) -------------------------------------------------
+    partial_actions = property(lambda self: self._partial_actions)
+    other_actions = property(lambda self: self._other_actions)
+    partial_vars = property(lambda self: self._partial_vars)
+    other_vars = property(lambda self: self._other_vars)
+    xdim = property(lambda self: self._xdim)
+    ydim = property(lambda self: self._ydim)
+    neq = property(lambda self: self._neq)
+    nineq = property(lambda self: self._nineq)
+    nknowns = property(lambda self: self._nknowns)
+    device = property(lambda self: self._device)
+
+    @property
+    def box_constraint(self):
+        return self.action_space.low, self.action_space.high
+
+    @property
+    def box_constraint_partial(self):
+        return self.action_space.low[self.partial_actions], self.action_space.high[self.partial_actions]
+
+    # ---- helpers ----------------------------------------------------------------------------------------
+    def _t(self, a):
+        if isinstance(a, torch.Tensor):
+            t = a.to(device=self._device, dtype=torch.float32)
+        else:
+            t = torch.as_tensor(np.asarray(a), dtype=torch.float32, device=self._device)
+        return t.view(1, -1) if t.dim() == 1 else t
+
+    def get_action_vars(self, action):                          # evopf.py:501-507
+        return (action[:, :self.ng], action[:, self.ng:2 * self.ng], action[:, 2 * self.ng:2 * self.ng + self.nbus],
+                action[:, -self.ne - self.nbus:-self.ne], action[:, -self.ne:])
+
+    # ---- hard-constraint protocol -----------------------------------------------------------------------
+    def complete_partial(self, state, action_partial):          # evopf.py:724-727
+        if action_partial.dim() == 1:
+            action_partial = action_partial.view(1, -1)
+        return _CompleteFn.apply(state[:, :self.xdim], action_partial, self.newton_tol, self.newton_max_iters)
+
+    def eq_resid(self, state, action):                          # evopf.py:520-546
+        return ops.evopf_resid(state, action, want_eq=True, want_ineq=False)[0]
+
+    def ineq_resid(self, state, action):                        # evopf.py:548-563
+        return ops.evopf_resid(state, action, want_eq=False, want_ineq=True)[1]
+
+    def ineq_dist(self, state, action):                         # evopf.py:565-567
+        return torch.clamp(self.ineq_resid(state, action), 0)
+
+    def ineq_partial_grad(self, state, action, eps=0.0):        # evopf.py:596-612 (eps is ignored there too)
+        return ops.evopf_direction(state, action)
+
+    def ineq_dist_np(self, state, action):                      # evopf.py:569-572
+        return self.ineq_dist(self._t(state), self._t(action)).cpu().numpy()
+
+    def eq_resid_np(self, state, action):                       # evopf.py:574-577
+        return self.eq_resid(self._t(state), self._t(action)).cpu().numpy()
+
+    # fused kernels used by rpo_b200.algo (no counterpart method in the reference: they fuse its call sequences)
+    def correct(self, state, action, lr, momentum, corr_eps, n_steps):
+        return ops.evopf_correct(state, action, lr, momentum, corr_eps, n_steps)
+
+    def project(self, state, action_partial, lr, momentum, corr_eps, n_steps):
+        if action_partial.dim() == 1:
+            action_partial = action_partial.view(1, -1)
+        yc, y, flags, _ = ops.evopf_project(state, action_partial, lr, momentum, corr_eps, n_steps, tol=self.newton_tol,
+                                            max_iters=self.newton_max_iters, want_y=True)
+        return yc, y, flags
+
+    def _unsupported(self, *a, **k):
+        raise NotImplementedError("eq_grad / ineq_grad / eq_jac / ineq_jac belong to corr_mode != 0, which no reference "
+                                  "script uses (SURVEY.md §8 a6); the B200 path implements corr_mode == 0")
+
+    eq_grad = ineq_grad = eq_jac = ineq_jac = _unsupported
+
+    # ---- volatile action box (evopf.py:769-783, Battery.update_bound :127-143) --------------------------
+    def update(self, state, full=False):
+        if isinstance(state, torch.Tensor):
+            s = state.detach().cpu().numpy()
+        else:
+            s = np.asarray(state)
+        if s.ndim == 1:
+            s = s.reshape(1, -1)
+        n = s.shape[0]
+        soc = s[:, -self.ne - self.nahead:-self.nahead]
+        new_p_max, new_p_min = self.evs.update_bound(soc)
+        low, high = self.box_constraint if full else self.box_constraint_partial
+        low = low[None].repeat(n, axis=0)
+        high = high[None].repeat(n, axis=0)
+        low[:, -self.ne:] = new_p_min
+        high[:, -self.ne:] = new_p_max
+        return low, high
+
+    def update_device(self, state: torch.Tensor):
+        """Same box as update(), computed on the device without a host round trip (float64 then rounded, as numpy does)."""
+        from ..synth import evopf_partial_box
+        return evopf_partial_box(state)
+
+    # ---- gym API (evopf.py:348-380) -----------------------------------------------------------------------
+    def reset(self):
+        state_grid, _ = self.data.reset()
+        state_evs = self.evs.reset()
+        self.state = np.concatenate([state_grid, state_evs])
+        self.action = None
+        return self.state.copy()
+
+    def step(self, action):
+        action = np.asarray(action)
+        price_next, _ = self.p_data.fetch()
+        price_next = price_next / self.baseMVA
+        grid_next, done = self.data.fetch()
+        exo = np.concatenate([grid_next, price_next]).astype(np.float32)
+        ns, rew, eqv, iqv = ops.evopf_step(self._t(self.state), self._t(action), self._t(exo))
+        next_state = ns[0].double().cpu().numpy()
+        info = {"ineq_viol": iqv.cpu().numpy(), "eq_viol": eqv.cpu().numpy()}
+        self.state = next_state
+        self.evs.state = next_state[28:].copy()
+        self.action = action
+        return next_state, float(rew[0].item()), done, info
+
+    def step_batch(self, state, action, next_exo):
+        """Vectorised step over independent replicas: (B,57), (B,43), (B,52) device tensors -> next_state, reward,
+        eq_viol, ineq_viol (all device tensors); the exogenous rows come from the caller's loaders / generators."""
+        return ops.evopf_step(state, action, next_exo)
+
+    def render(self, mode="human"):
+        raise NotImplementedError("rendering is outside the hot path (SURVEY.md §2 #17)")
+
+    def close(self):
+        pass
+
+    def seed(self, seed=None):
+        return [seed]

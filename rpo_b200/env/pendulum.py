@@ -1,0 +1,134 @@
+"""SpringPendulum-v0 drop-in: the API of rpo.env.SpringPendulumEnv (rpo/env/classic_control/pendulum.py) over the kernels.
+
+Row-wise semantics: the reference's batched ineq_partial_grad multiplies (B,1) by (1,B) (pendulum.py:337-339) and so
+couples rows for B > 1; every kernel here evaluates a row as the reference evaluates a batch of one.
+The reference caches diff_eq* on the env between calls (pendulum.py:264-288); the kernels recompute them from the
+observation (5 flops), so this class is stateless between protocol calls.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import ops
+from .spaces import Box
+
+
+class _CompleteFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, obs, z):
+        ctx.save_for_backward(obs)
+        return ops.pen_complete_fwd(obs, z)
+
+    @staticmethod
+    def backward(ctx, dl_da):
+        (obs,) = ctx.saved_tensors
+        return None, ops.pen_complete_bwd(obs, dl_da.contiguous())
+
+
+class SpringPendulumEnv(object):
+    metadata = {"render_modes": ["human", "rgb_array"], "render_fps": 30}
+
+    def __init__(self, g=10.0, device=None):
+        self.max_speed, self.max_torque, self.max_length_delta = 8.0, 6.0, 0.5
+        self.max_summation = 32.0
+        self.dt, self.g, self.m, self.k, self.l0 = 0.05, g, 0.5, 1.0, 1.0
+        if g != 10.0:
+            raise NotImplementedError("the kernels bake g = 10 (the value every reference script uses)")
+        self.m_dt = self.m / self.dt
+        high = np.array([1.0, 1.0, self.max_speed, 1.5, 0.05], dtype=np.float32)
+        low = np.array([-1.0, -1.0, -self.max_speed, 0.5, -0.05], dtype=np.float32)
+        ah = self.max_torque * np.array([1.0, 1.0], dtype=np.float32)
+        self.action_space = Box(low=-ah, high=ah, shape=(2,), dtype=np.float32)
+        self.observation_space = Box(low=low, high=high, dtype=np.float32)
+        self.state_dim, self.action_dim, self.eq_num, self.ineq_num = 5, 2, 1, 1
+        self.fx_idx, self.fy_idx = 0, 1
+        self.seed()
+        self.partial_actions = np.array([0])
+        self.other_actions = np.setdiff1d(np.arange(self.action_dim), self.partial_actions)
+        self.device = torch.device(device) if device is not None else torch.device("cuda")
+        self.counter = None
+        self.volatile = False
+        self.update = None
+        self.state = None
+
+    def seed(self, seed=None):
+        self.np_random = np.random.RandomState(seed)
+        return [seed]
+
+    def _t(self, a):
+        t = a.to(device=self.device, dtype=torch.float32) if isinstance(a, torch.Tensor) else \
+            torch.as_tensor(np.asarray(a), dtype=torch.float32, device=self.device)
+        return t.view(1, -1) if t.dim() == 1 else t
+
+    # ---- hard-constraint protocol (pendulum.py:256-343) ---------------------------------------------------
+    def complete_partial(self, state, action_partial):
+        z = action_partial.view(-1, 1) if action_partial.dim() == 1 else action_partial
+        return _CompleteFn.apply(state, z)
+
+    def eq_resid(self, state, action):
+        return ops.pen_resid(state, action, want_ineq=False)[0]
+
+    def ineq_resid(self, state, action):
+        return ops.pen_resid(state, action, want_eq=False)[1]
+
+    def eq_dist(self, state, action):
+        return torch.abs(self.eq_resid(state, action))
+
+    def ineq_dist(self, state, action):
+        return torch.clamp(self.ineq_resid(state, action), 0)
+
+    def ineq_partial_grad(self, state, action, eps=0):
+        return ops.pen_direction(state, action)
+
+    def ineq_dist_np(self, state, action):
+        return self.ineq_dist(self._t(state), self._t(action)).cpu().numpy()
+
+    def eq_resid_np(self, state, action):
+        return self.eq_resid(self._t(state), self._t(action)).cpu().numpy()
+
+    def correct(self, state, action, lr, momentum, corr_eps, n_steps):
+        return ops.pen_correct(state, action, lr, momentum, corr_eps, n_steps)
+
+    def project(self, state, action_partial, lr, momentum, corr_eps, n_steps):
+        z = action_partial.view(-1, 1) if action_partial.dim() == 1 else action_partial
+        ac, a, flags = ops.pen_project(state, z, lr, momentum, corr_eps, n_steps, want_a=True)
+        return ac, a, flags
+
+    @property
+    def box_constraint(self):
+        return self.action_space.low, self.action_space.high
+
+    @property
+    def box_constraint_partial(self):
+        return self.action_space.low[self.partial_actions], self.action_space.high[self.partial_actions]
+
+    # ---- gym API (pendulum.py:80-140) ----------------------------------------------------------------------
+    def reset(self):
+        high = np.array([np.pi / 12, 1.0, 1.05, 0.05], dtype=np.float32)
+        low = np.array([-np.pi / 12, -1.0, 0.95, -0.05], dtype=np.float32)
+        self.state = self.np_random.uniform(low=low, high=high)
+        self.counter = 0
+        return self._get_obs()
+
+    def _get_obs(self):
+        theta, thetadot, l, ldot = self.state
+        return np.array([np.cos(theta), np.sin(theta), thetadot, l, ldot])
+
+    def step(self, action):
+        self.counter += 1
+        action = np.asarray(action, dtype=np.float32)
+        nst, nobs, rew, done, eqv, iqv = ops.pen_step(self._t(self.state), self._t(action))
+        self.state = nst[0].double().cpu().numpy()
+        info = {"ineq_viol": iqv.cpu().numpy(), "eq_viol": eqv.cpu().numpy()}
+        return nobs[0].double().cpu().numpy(), float(rew[0].item()), bool(done[0].item()), info
+
+    def step_batch(self, st, action):
+        """(B,4) internal states, (B,2) actions -> next_st, next_obs, reward, done(int32), eq_viol, ineq_viol."""
+        return ops.pen_step(st, action)
+
+    def render(self, mode="human"):
+        raise NotImplementedError("rendering is outside the hot path")
+
+    def close(self):
+        pass

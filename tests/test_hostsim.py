@@ -1,0 +1,135 @@
+"""The per-instance device code (rpo_b200/csrc/*_core.cuh + generated evopf_gen.cuh) compiled for the HOST by g++
+(tests/hostsim) and checked against the oracle: validates the generated sparse LU / Newton / GRG math on a box
+without a GPU.  float64 build: formulas to ~1e-9; float32 build: the tolerances the GPU tests use."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from tests.parity import GRAD_RTOL, Y_RTOL, assert_close_or_marginal, rel_err
+
+HS = os.path.join(os.path.dirname(__file__), "hostsim")
+
+
+@pytest.fixture(scope="module")
+def libs():
+    subprocess.check_call(["make", "-s", "-C", HS])
+    out = {}
+    for prec in ("f32", "f64"):
+        lib = ctypes.CDLL(os.path.join(HS, "libhostsim_%s.so" % prec))
+        assert lib.hs_sizeof_real() == (4 if prec == "f32" else 8)
+        out[prec] = lib
+    return out
+
+
+def _P(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _complete(lib, st, z, npd, creal, tol=1e-5):
+    B = st.shape[0]
+    y = np.zeros((B, 43), npd)
+    status = np.zeros(B, np.int32)
+    lib.hs_evopf_complete(_P(st), st.shape[1], _P(z), _P(y), B, creal(tol), 50, _P(status))
+    return y, status
+
+
+@pytest.mark.parametrize("dist", ["D1", "D2"])
+def test_generated_math_float64_exact(libs, dist):
+    from oracle.rpo_oracle import EvopfOracle, grad_steps
+    from rpo_b200 import synth
+    lib, orc = libs["f64"], EvopfOracle(dtype=torch.float64, const_dtype=torch.float32)
+    B = 400
+    st = synth.evopf_states(B, seed=3).double()
+    z = synth.evopf_partial_actions(st.float(), seed=4, dist=dist).double()
+    s_np, z_np = st.numpy().copy(), z.numpy().copy()
+    y, status = _complete(lib, s_np, z_np, np.float64, ctypes.c_double, tol=1e-13)
+    y_o, jac, inv, _ = orc.complete_partial_fwd(st, z, tol=1e-13, return_saved=True)
+    assert (status >> 8).max() == 0
+    assert rel_err(torch.tensor(y), y_o).max() < 1e-10
+    g = synth.upstream_grad(B, 43, seed=5).double().numpy().copy()
+    dz, dx = np.zeros((B, 14)), np.zeros((B, 28))
+    yo = y_o.numpy().copy()
+    lib.hs_evopf_backward(_P(yo), _P(g), _P(dz), _P(dx), B)
+    # the oracle keeps the Jacobian of the last PRE-update iterate (evopf.py:838); at tol 1e-13 both coincide
+    dx_o, dz_o = orc.complete_partial_bwd(torch.tensor(g), jac, inv)
+    assert rel_err(torch.tensor(dz), dz_o).max() < 1e-8 and rel_err(torch.tensor(dx), dx_o).max() < 1e-8
+    out, em, im = np.zeros((B, 43)), np.zeros(B), np.zeros(B)
+    lib.hs_evopf_direction(_P(s_np), 57, _P(yo), _P(out), _P(em), _P(im), B)
+    d_o = orc.ineq_partial_grad(st, y_o)
+    assert rel_err(torch.tensor(out), d_o).max() < 1e-9
+    assert np.abs(em - orc.eq_resid(st, y_o).abs().max(1).values.numpy()).max() < 1e-12
+    # float32 inputs converted to float64: battery bounds are rounded to `real` = double here, so compare loosely
+    assert np.abs(im - orc.ineq_dist(st, y_o).max(1).values.numpy()).max() < 1e-7
+    yc = yo.copy()
+    flags = np.zeros(10, np.int32)
+    lib.hs_evopf_correct(_P(s_np), 57, _P(yc), B, ctypes.c_double(1e-4), ctypes.c_double(0.0), ctypes.c_double(1e-5), 10, _P(flags))
+    yc_o, k = grad_steps(orc, st, y_o, 1e-4, 0.0, 1e-5, 10)
+    assert k == 10 and flags.tolist() == [1] * 10
+    assert rel_err(torch.tensor(yc), yc_o).max() < 1e-7
+    eq, iq = np.zeros((B, 28)), np.zeros((B, 58))
+    lib.hs_evopf_resid(_P(s_np), 57, _P(yc), _P(eq), _P(iq), B)
+    assert (torch.tensor(eq) - orc.eq_resid(st, torch.tensor(yc))).abs().max() < 1e-12
+
+
+@pytest.mark.parametrize("dist", ["D1", "D2"])
+def test_generated_math_float32_tolerances(libs, dist, evopf_oracle, evopf_oracle64):
+    from oracle.rpo_oracle import grad_steps_margins
+    from rpo_b200 import synth
+    lib, orc = libs["f32"], evopf_oracle
+    B = 3000
+    st = synth.evopf_states(B, seed=11)
+    z = synth.evopf_partial_actions(st, seed=12, dist=dist)
+    s_np, z_np = st.numpy().copy(), z.numpy().copy()
+    y, status = _complete(lib, s_np, z_np, np.float32, ctypes.c_float)
+    y_o, jac, inv, _ = orc.complete_partial_fwd(st, z, return_saved=True)
+    assert (status >> 8).max() == 0 and (status & 0xff).max() <= 8
+    yt = torch.tensor(y)
+    assert rel_err(yt, y_o).max() <= Y_RTOL
+    r = evopf_oracle64.eq_resid(st.double(), yt.double()).abs().max(1).values
+    assert r.max() <= 1.5e-5 and (r > 1e-5).double().mean() <= 1e-3
+    g = synth.upstream_grad(B, 43, seed=13).numpy().copy()
+    dz, dx = np.zeros((B, 14), np.float32), np.zeros((B, 28), np.float32)
+    lib.hs_evopf_backward(_P(y), _P(g), _P(dz), _P(dx), B)
+    dx_o, dz_o = orc.complete_partial_bwd(torch.tensor(g), jac, inv)
+    assert rel_err(torch.tensor(dz), dz_o).max() <= GRAD_RTOL and rel_err(torch.tensor(dx), dx_o).max() <= GRAD_RTOL
+    yc = y.copy()
+    flags = np.zeros(10, np.int32)
+    lib.hs_evopf_correct(_P(s_np), 57, _P(yc), B, ctypes.c_float(1e-4), ctypes.c_float(0.0), ctypes.c_float(1e-5), 10, _P(flags))
+    yc_o, k, margin = grad_steps_margins(orc, st, y_o, 1e-4, 0.0, 1e-5, 10)
+    assert_close_or_marginal(rel_err(torch.tensor(yc), yc_o), margin, Y_RTOL)
+
+
+def test_hostsim_matches_reference_goldens(libs):
+    lib = libs["f32"]
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "evopf_D1.npz"))
+    st, z = g["state"].copy(), g["z"].copy()
+    y, status = _complete(lib, st, z, np.float32, ctypes.c_float)
+    assert rel_err(torch.tensor(y), torch.tensor(g["y"])).max() <= Y_RTOL
+    B = st.shape[0]
+    dz, dx = np.zeros((B, 14), np.float32), np.zeros((B, 28), np.float32)
+    yg, gg = g["y"].copy(), g["g"].copy()
+    lib.hs_evopf_backward(_P(yg), _P(gg), _P(dz), _P(dx), B)
+    assert rel_err(torch.tensor(dz), torch.tensor(g["dz"])).max() <= GRAD_RTOL
+    assert rel_err(torch.tensor(dx), torch.tensor(g["dx"])).max() <= GRAD_RTOL
+    yc = yg.copy()
+    lib.hs_evopf_correct(_P(st), 57, _P(yc), B, ctypes.c_float(1e-4), ctypes.c_float(0.0), ctypes.c_float(1e-5), 10, None)
+    assert rel_err(torch.tensor(yc), torch.tensor(g["y_corr"])).max() <= Y_RTOL
+    ycm = yg.copy()
+    lib.hs_evopf_correct(_P(st), 57, _P(ycm), B, ctypes.c_float(1e-4), ctypes.c_float(0.5), ctypes.c_float(1e-5), 5, None)
+    assert rel_err(torch.tensor(ycm), torch.tensor(g["y_corr_mom"])).max() <= Y_RTOL
+
+
+def test_infeasible_power_flow_is_flagged(libs, evopf_oracle):
+    """A collapsed-voltage instance (found at index 397174 of seed 0): the reference's Newton diverges silently
+    (evopf.py:837 discards `converged`); the kernel code reports NOT_CONVERGED in the status word."""
+    from rpo_b200 import synth
+    st = synth.evopf_states(1 << 20, seed=0)[397174:397175].clone()
+    z = synth.evopf_partial_actions(synth.evopf_states(1 << 20, seed=0), seed=1)[397174:397175].clone()
+    y, status = _complete(libs["f32"], st.numpy().copy(), z.numpy().copy(), np.float32, ctypes.c_float)
+    assert (status[0] & 0xff) == 50 and (status[0] & 0x100)
+    y_o, _, _, iters = evopf_oracle.complete_partial_fwd(st, z, return_saved=True)
+    assert iters == [50]

@@ -30,7 +30,7 @@ from rpo_b200 import evopf_constants as K  # noqa: E402
 def lit(x: float) -> str:
     """f32-rounded literal wrapped in RC() so the same header can be compiled in double for validation."""
     v = float(np.float32(x))
-    return "RC(%.9g)" % v
+    return "RC(%.17g)" % v
 
 
 class Gen(object):
