@@ -149,8 +149,10 @@ def run_reference(args, rank: int):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "EVOPF-v0 completion + 10 correction steps + GRG backward, synthetic D1 inputs",
-                   "instances_per_step": n_step, "device": "cpu"},
+        "config": {"workload": "synthetic EVOPF-v0 completion+correction (fwd+bwd), batch 2^%d instances per GPU" % args.log2_batch,
+                   "reference_sample": "each step times %d instances of that workload on the host CPU (bounded sample)" % n_step,
+                   "input_dist": "D1 (uniform in the state-dependent partial box)", "newton": NEWTON, "correction": CORR,
+                   "device": "cpu"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "%d instances per step, chunks of 1024, torch CPU oracle port of the reference path" % n_step},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

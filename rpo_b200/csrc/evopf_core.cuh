@@ -64,3 +64,75 @@ RPO_HD bool evopf_correct_step(const real* x, const real* pe_max, const real* pe
     }
     return (eqmax > corr_eps) || (ineqmax > corr_eps);
 }
+
+// Fused projection = complete_partial followed by n_steps >= 1 correction steps (RPODDPG.process_action,
+// rpo_ddpg.py:72-77) as ONE loop whose body holds a single copy of the two big shared pieces (point evaluation and
+// sparse LU): a Newton iteration and a correction step differ only in what follows the factorisation.  Besides
+// removing the completion's separate tail evaluation (the first correction pass evaluates the final Newton point
+// anyway), this halves the instruction footprint of the fused kernel, which is instruction-fetch sensitive
+// (DESIGN.md §5).  The phase switch is uniform over the voting group, so there is no divergence.
+//   any(pred)        vote over the lanes that iterate together
+//   on_y(y, status)  called once, by every lane, when the completion output is final (before the first step)
+//   on_flag(k, unsat) called once per correction step with this lane's loop-test result
+//   scratch          >= EVOPF_SCRATCH reals of per-lane storage for values that are cold during the factorisation
+//                    (violation signs d[43], battery bounds): shared memory on the device, a local array on the host
+#define EVOPF_SCRATCH 53
+template <bool MOMENTUM, class Vote, class OnY, class OnFlag>
+RPO_HD void evopf_project_loop(const real* x, const real* z, real* y, real* scratch, real tol, int max_iters, real lr,
+                               real momentum, real corr_eps, int n_steps, Vote any, OnY on_y, OnFlag on_flag) {
+    real* d = scratch;
+    real* pe_max = scratch + 43;
+    real* pe_min = scratch + 48;
+    evopf_pe_bounds(x + 28, pe_max, pe_min);
+    real prev[MOMENTUM ? 43 : 1];
+    if (MOMENTUM) {
+        for (int i = 0; i < 43; ++i) prev[i] = RC(0.0);
+    }
+    evopf_init(z, y);
+    int it = 0, k = 0;
+    int newton = 1;
+    bool conv = false, first = true;
+    real minpiv = RC(3.0e38);
+    while (true) {
+        RPO_OPAQUE(newton);
+        EvopfPt pt;
+        real lu[EVOPF_NLU], ipiv[EVOPF_NN], eqmax = RC(0.0), ineqmax = RC(0.0);
+        evopf_eval_full(y, pt);
+        if (!newton) {
+            if (first) {
+                evopf_tail(x, y, pt);
+                int st = it & RPO_ST_ITERS_MASK;
+                if (!conv) st |= RPO_ST_NOT_CONVERGED;
+                if (!(minpiv >= RPO_PIVOT_FLOOR)) st |= RPO_ST_SMALL_PIVOT;
+                on_y(y, st);
+                first = false;
+            }
+            eqmax = evopf_eq_resid(x, y, pt, (real*)0);
+            ineqmax = evopf_ineq(pe_max, pe_min, y, (real*)0, d);
+        }
+        const real mp = evopf_factor(pt, lu, ipiv);
+        if (newton) {
+            real r[EVOPF_NN];
+            minpiv = FMIN(minpiv, mp);
+            evopf_newton_rhs(x, y, pt, r);
+            evopf_solve(lu, ipiv, r);
+            const real n2 = evopf_newton_update(r, y);
+            ++it;
+            conv = sqrt(n2) < tol;
+            if (!any(!conv) || it >= max_iters) newton = 0;
+        } else {
+            real dir[43];
+            evopf_direction_post(y, pt, lu, ipiv, d, dir);
+            for (int i = 0; i < 43; ++i) {
+                real s = lr * dir[i];
+                if (MOMENTUM) {
+                    s = s + momentum * prev[i];
+                    prev[i] = s;
+                }
+                y[i] = y[i] - s;
+            }
+            on_flag(k, (eqmax > corr_eps) || (ineqmax > corr_eps));
+            if (++k >= n_steps) break;
+        }
+    }
+}

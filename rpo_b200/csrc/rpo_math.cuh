@@ -24,6 +24,15 @@ typedef RPO_REAL real;
 
 #define RC(x) ((real)(x))
 
+// Hides an integer from the optimiser (no instruction emitted).  Used on the phase flag of evopf_project_loop so that
+// the compiler cannot split the single loop back into two specialised loops (jump threading), which would duplicate
+// the shared evaluation + LU code the loop exists to share.
+#if defined(__GNUC__) || defined(__CUDACC__)
+#define RPO_OPAQUE(x) asm volatile("" : "+r"(x))
+#else
+#define RPO_OPAQUE(x) do { } while (0)
+#endif
+
 // RPO_ALIGN(n): markers the generator drops every 32 statements of the big straight-line functions.  On the device,
 // when RPO_ALIGN_EVERY > 0, every RPO_ALIGN_EVERY-th marker is a block barrier that keeps the warps of a CTA within
 // one instruction-cache window of each other (the kernels are instruction-fetch bound).

@@ -54,5 +54,30 @@ void hs_evopf_resid(const real* state, int ld, const real* y, real* eq, real* in
     }
 }
 
+struct HsOnY {
+    real* y_out; int* status;
+    void operator()(const real* y, int st) const {
+        if (y_out) for (int i = 0; i < 43; ++i) y_out[i] = y[i];
+        if (status) *status = st;
+    }
+};
+struct HsOnFlag {
+    int* flags;
+    void operator()(int k, bool unsat) const { if (flags && unsat) flags[k] = 1; }
+};
+
+// fused single-loop projection (evopf_project_loop): y (nullable) = completion output, yc = corrected action
+void hs_evopf_project(const real* state, int ld, const real* z, real* y, real* yc, int B, real tol, int max_iters, real lr,
+                      real momentum, real corr_eps, int n_steps, int* flags, int* status) {
+    for (int b = 0; b < B; ++b) {
+        real yy[43], scratch[EVOPF_SCRATCH];
+        HsOnY oy = {y ? y + (long)b * 43 : (real*)0, status ? status + b : (int*)0};
+        HsOnFlag of = {flags};
+        evopf_project_loop<true>(state + (long)b * ld, z + (long)b * 14, yy, scratch, tol, max_iters, lr, momentum, corr_eps, n_steps,
+                                 RpoVoteSelf(), oy, of);
+        for (int i = 0; i < 43; ++i) yc[(long)b * 43 + i] = yy[i];
+    }
+}
+
 int hs_sizeof_real() { return (int)sizeof(real); }
 }

@@ -22,8 +22,8 @@ def test_cart_golden(p):
     dz = ops.cart_complete_bwd(torch.tensor(g["g"]).cuda(), p)
     assert np.abs(dz.cpu().numpy() - g["dz"]).max() <= 1e-6
     eq, iq = ops.cart_resid(a)
-    assert np.abs(eq.cpu().numpy() - g["eq_resid"]).max() <= 2e-6
-    assert np.abs(iq.cpu().numpy() - g["ineq_resid"]).max() <= 2e-6
+    assert np.abs(eq.cpu().numpy() - g["eq_resid"]).max() <= 4e-6          # 2 ulp at |resid| ~ 30
+    assert np.abs(iq.cpu().numpy() - g["ineq_resid"]).max() <= 4e-6
     d = ops.cart_direction(torch.tensor(g["a"]).cuda(), p)
     assert np.abs(d.cpu().numpy() - g["dir"]).max() <= 1e-5
     ac, flags = ops.cart_correct(torch.tensor(g["a"]).cuda(), p, 2e-2, 0.0, 1e-5, 10)

@@ -133,3 +133,23 @@ def test_infeasible_power_flow_is_flagged(libs, evopf_oracle):
     assert (status[0] & 0xff) == 50 and (status[0] & 0x100)
     y_o, _, _, iters = evopf_oracle.complete_partial_fwd(st, z, return_saved=True)
     assert iters == [50]
+
+
+def test_fused_single_loop_equals_complete_then_correct(libs):
+    """evopf_project_loop (one loop, shared eval+LU code) must equal evopf_complete followed by the correction steps
+    bit for bit: same arithmetic, only the code layout differs."""
+    from rpo_b200 import synth
+    lib = libs["f32"]
+    B = 500
+    st = synth.evopf_states(B, seed=21).numpy().copy()
+    z = synth.evopf_partial_actions(torch.tensor(st), seed=22).numpy().copy()
+    y, status = _complete(lib, st, z, np.float32, ctypes.c_float)
+    yc = y.copy()
+    flags = np.zeros(10, np.int32)
+    lib.hs_evopf_correct(_P(st), 57, _P(yc), B, ctypes.c_float(1e-4), ctypes.c_float(0.5), ctypes.c_float(1e-5), 7, _P(flags))
+    y2, yc2 = np.zeros_like(y), np.zeros_like(y)
+    status2, flags2 = np.zeros(B, np.int32), np.zeros(10, np.int32)
+    lib.hs_evopf_project(_P(st), 57, _P(z), _P(y2), _P(yc2), B, ctypes.c_float(1e-5), 50, ctypes.c_float(1e-4),
+                         ctypes.c_float(0.5), ctypes.c_float(1e-5), 7, _P(flags2), _P(status2))
+    assert np.array_equal(y, y2) and np.array_equal(yc, yc2)
+    assert np.array_equal(status, status2) and np.array_equal(flags, flags2)

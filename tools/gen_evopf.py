@@ -205,20 +205,17 @@ class Gen(object):
                             e("    const real t1d_ = FMA(pt.vr[%d], al%d, pt.vi[%d] * be%d);" % (i, k, i, k))
                             e("    const real t2d_ = FMA(pt.vi[%d], al%d, -(pt.vr[%d] * be%d));" % (i, k, i, k))
                     else:
-                        if first:
-                            if g != 0:
-                                e("    a_ = FMA(%s, pt.vr[%d], %s * pt.vi[%d]);" % (lit(g), j, lit(-b), j))
-                                e("    b_ = FMA(%s, pt.vr[%d], %s * pt.vi[%d]);" % (lit(b), j, lit(g), j))
-                            else:
-                                e("    a_ = %s * pt.vi[%d];" % (lit(-b), j))
-                                e("    b_ = %s * pt.vr[%d];" % (lit(b), j))
+                        # same operation order as the full variant, so that flows agree bit for bit
+                        if g != 0:
+                            e("    const real al%d = FMA(%s, pt.vr[%d], %s * pt.vi[%d]);" % (k, lit(g), j, lit(-b), j))
+                            e("    const real be%d = FMA(%s, pt.vr[%d], %s * pt.vi[%d]);" % (k, lit(b), j, lit(g), j))
                         else:
-                            if g != 0:
-                                e("    a_ = FMA(%s, pt.vr[%d], a_); a_ = FMA(%s, pt.vi[%d], a_);" % (lit(g), j, lit(-b), j))
-                                e("    b_ = FMA(%s, pt.vr[%d], b_); b_ = FMA(%s, pt.vi[%d], b_);" % (lit(b), j, lit(g), j))
-                            else:
-                                e("    a_ = FMA(%s, pt.vi[%d], a_);" % (lit(-b), j))
-                                e("    b_ = FMA(%s, pt.vr[%d], b_);" % (lit(b), j))
+                            e("    const real al%d = %s * pt.vi[%d];" % (k, lit(-b), j))
+                            e("    const real be%d = %s * pt.vr[%d];" % (k, lit(b), j))
+                        if first:
+                            e("    a_ = al%d; b_ = be%d;" % (k, k))
+                        else:
+                            e("    a_ += al%d; b_ += be%d;" % (k, k))
                     first = False
                 e("    pt.P[%d] = FMA(pt.vr[%d], a_, pt.vi[%d] * b_);" % (i, i, i))
                 e("    pt.Q[%d] = FMA(pt.vi[%d], a_, -(pt.vr[%d] * b_));" % (i, i, i))
@@ -309,11 +306,8 @@ class Gen(object):
 
     def gen_newton(self):
         e = self.emit
-        e("// One Newton iteration of the completion (PFFunctionFn.forward evopf.py:826-835): y's Newton unknowns are")
-        e("// updated in place; returns ||delta||_2^2 of the *unscaled* update.  pd/qd = x[0:14], x[14:28].")
-        e("RPO_HD real evopf_newton_iter(const real* x, real* y, EvopfPt& pt, real* minpiv) {")
-        e("    real lu[EVOPF_NLU], ipiv[EVOPF_NN], r[EVOPF_NN];")
-        e("    evopf_eval_full(y, pt);")
+        e("// Newton right-hand side r[k] = injection - flow of equation k (elimination order), from an evaluated point.")
+        e("RPO_HD void evopf_newton_rhs(const real* x, const real* y, const EvopfPt& pt, real* r) {")
         for k, (kind, i) in enumerate(self.eqs):
             if kind == "P":
                 if i in self.pv:
@@ -323,8 +317,10 @@ class Gen(object):
                     e("    r[%d] = (-x[%d]) - pt.P[%d];" % (k, i, i))
             else:
                 e("    r[%d] = (-x[%d]) - pt.Q[%d];" % (k, 14 + i, i))
-        e("    *minpiv = evopf_factor(pt, lu, ipiv);")
-        e("    evopf_solve(lu, ipiv, r);")
+        e("}")
+        e("")
+        e("// Apply the solved (scaled) Newton step to y; returns ||delta||_2^2 of the unscaled update.")
+        e("RPO_HD real evopf_newton_update(const real* r, real* y) {")
         e("    real n2 = RC(0.0);")
         for k, (kind, j) in enumerate(self.unk):
             if kind == "th":
@@ -332,6 +328,17 @@ class Gen(object):
             else:
                 e("    { const real dv_ = y[%d] * r[%d]; y[%d] += dv_; n2 = FMA(dv_, dv_, n2); }" % (K.VM0 + j, k, K.VM0 + j))
         e("    return n2;")
+        e("}")
+        e("")
+        e("// One Newton iteration of the completion (PFFunctionFn.forward evopf.py:826-835): y's Newton unknowns are")
+        e("// updated in place; returns ||delta||_2^2 of the *unscaled* update.  pd/qd = x[0:14], x[14:28].")
+        e("RPO_HD real evopf_newton_iter(const real* x, real* y, EvopfPt& pt, real* minpiv) {")
+        e("    real lu[EVOPF_NLU], ipiv[EVOPF_NN], r[EVOPF_NN];")
+        e("    evopf_eval_full(y, pt);")
+        e("    evopf_newton_rhs(x, y, pt, r);")
+        e("    *minpiv = evopf_factor(pt, lu, ipiv);")
+        e("    evopf_solve(lu, ipiv, r);")
+        e("    return evopf_newton_update(r, y);")
         e("}")
         e("")
         e("// Step 0 of the completion: scatter z, flat start (evopf.py:794-807).")
@@ -507,12 +514,9 @@ class Gen(object):
         e("// Reduced correction direction = EVOPFEnv.ineq_partial_grad (evopf.py:596-612) in two-solve form")
         e("// (SURVEY App. B.4) on the 22x22 Newton block (28x28 J_O is block triangular, SURVEY H3).")
         e("// Also evaluates the loop test of grad_steps (rpo_ddpg.py:271-272): *eqmax = max|eq_resid|, *ineqmax = max ineq_dist.")
-        e("RPO_HD real evopf_direction(const real* x, const real* pe_max, const real* pe_min, const real* y, real* out, real* eqmax, real* ineqmax) {")
-        e("    EvopfPt pt; real lu[EVOPF_NLU], ipiv[EVOPF_NN], rhs[EVOPF_NN], d[43], tL[6], tP[14], tQ[14], cs[6], q[28];")
-        e("    evopf_eval_full(y, pt);")
-        e("    *eqmax = evopf_eq_resid(x, y, pt, (real*)0);")
-        e("    *ineqmax = evopf_ineq(pe_max, pe_min, y, (real*)0, d);")
-        e("    const real minpiv = evopf_factor(pt, lu, ipiv);")
+        e("// post-factor part of the direction: d = sign-of-violation vector (43), lu/ipiv = factors of the Newton block at y")
+        e("RPO_HD void evopf_direction_post(const real* y, const EvopfPt& pt, const real* lu, const real* ipiv, const real* d, real* out) {")
+        e("    real rhs[EVOPF_NN], tL[6], tP[14], tQ[14], cs[6], q[28];")
         e("    tL[0] = d[%d];" % (K.PG0 + 0))
         for gi in range(K.NG):
             e("    tL[%d] = d[%d];" % (1 + gi, K.QG0 + gi))
@@ -588,6 +592,15 @@ class Gen(object):
                 e("    out[%d] = -rhs[%d];" % (K.VA0 + j, c))
             else:
                 e("    out[%d] = -(y[%d] * rhs[%d]);" % (K.VM0 + j, K.VM0 + j, c))
+        e("}")
+        e("")
+        e("RPO_HD real evopf_direction(const real* x, const real* pe_max, const real* pe_min, const real* y, real* out, real* eqmax, real* ineqmax) {")
+        e("    EvopfPt pt; real lu[EVOPF_NLU], ipiv[EVOPF_NN], d[43];")
+        e("    evopf_eval_full(y, pt);")
+        e("    *eqmax = evopf_eq_resid(x, y, pt, (real*)0);")
+        e("    *ineqmax = evopf_ineq(pe_max, pe_min, y, (real*)0, d);")
+        e("    const real minpiv = evopf_factor(pt, lu, ipiv);")
+        e("    evopf_direction_post(y, pt, lu, ipiv, d, out);")
         e("    return minpiv;")
         e("}")
         e("")
