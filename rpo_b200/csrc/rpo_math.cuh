@@ -69,6 +69,21 @@ RPO_HD void rpo_sincosf(float x, float* sp, float* cp) {
     *cp = ((q + 1) & 2) ? -cc : cc;
 }
 
+// sincos without range reduction for |x| <= 1.6 (pi/2 + margin): near-minimax fits of (sin x - x)/x^3 and
+// (cos x - 1)/x^2 in x^2 (max abs error 1.5e-7 over the interval, evaluated in float32); 11 FP32 instructions.
+RPO_HD void rpo_sincosf_small(float x, float* sp, float* cp) {
+    const float x2 = x * x;
+    float ps = fmaf(x2, 0x1.60ff98p-19f, -0x1.9fae94p-13f);
+    ps = fmaf(ps, x2, 0x1.111036p-7f);
+    ps = fmaf(ps, x2, -0x1.555554p-3f);
+    *sp = fmaf(x * x2, ps, x);
+    float pc = fmaf(x2, -0x1.19d6b8p-22f, 0x1.9f9cb4p-16f);
+    pc = fmaf(pc, x2, -0x1.6c14f8p-10f);
+    pc = fmaf(pc, x2, 0x1.55555p-5f);
+    pc = fmaf(pc, x2, -0.5f);
+    *cp = fmaf(pc, x2, 1.0f);
+}
+
 #if defined(__CUDA_ARCH__)
 // device, float only (the CUDA build is always float)
 RPO_D float rpo_rcp_approx(float x) {
@@ -78,6 +93,7 @@ RPO_D float rpo_rcp_approx(float x) {
 }
 #define FMA(a, b, c) __fmaf_rn((a), (b), (c))
 #define SINCOS(x, s, c) rpo_sincosf((x), (s), (c))
+#define SINCOS_SMALL(x, s, c) rpo_sincosf_small((x), (s), (c))
 #define RCP(x) rpo_rcp_approx(x)
 #define FMIN(a, b) fminf((a), (b))
 #define FMAX(a, b) fmaxf((a), (b))
@@ -87,8 +103,11 @@ static inline float rpo_fma_(float a, float b, float c) { return fmaf(a, b, c); 
 static inline double rpo_fma_(double a, double b, double c) { return fma(a, b, c); }
 static inline void rpo_sincos_(float x, float* s, float* c) { rpo_sincosf(x, s, c); }
 static inline void rpo_sincos_(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
+static inline void rpo_sincos_small_(float x, float* s, float* c) { rpo_sincosf_small(x, s, c); }
+static inline void rpo_sincos_small_(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
 #define FMA(a, b, c) rpo_fma_((real)(a), (real)(b), (real)(c))
 #define SINCOS(x, s, c) rpo_sincos_((x), (s), (c))
+#define SINCOS_SMALL(x, s, c) rpo_sincos_small_((x), (s), (c))
 #define RCP(x) (RC(1.0) / (x))
 #define FMIN(a, b) ((a) < (b) ? (a) : (b))
 #define FMAX(a, b) ((a) > (b) ? (a) : (b))
