@@ -265,7 +265,7 @@ def main():
     # end-to-end through the host-buffer API: pinned host inputs -> H2D -> kernels -> D2H results, every step
     e2e = None
     if not args.no_e2e:
-        hp = HostProjector(dev, chunk=1 << 16, n_streams=4, corr_lr=CORR["lr"], momentum=CORR["momentum"],
+        hp = HostProjector(dev, chunk=1 << 17, n_streams=4, corr_lr=CORR["lr"], momentum=CORR["momentum"],
                            corr_eps=CORR["corr_eps"], n_steps=CORR["n_steps"], **NEWTON)
         pst, pz, pg = st_h.pin_memory(), z_h.pin_memory(), g_h.pin_memory()
         yc_out, dz_out = hp.pinned(B, 43), hp.pinned(B, 14)

@@ -130,6 +130,14 @@ int rpo_pen_resid(const float* obs, const float* a, float* eq, float* ineq, int6
 int rpo_pen_step(const float* st, const float* a, float* next_st, float* next_obs, float* reward, int32_t* done,
                  float* eq_viol, float* ineq_viol, int64_t B, void* stream);
 
+/* ------------------------------------------------------------------ host-buffer helpers ----------------------- */
+/* Copy the first `ncols` floats of each of `nrows` rows between a HOST matrix (pinned for asynchrony; leading dimension
+ * ld_host floats) and a DEVICE matrix (leading dimension ld_dev floats): one strided DMA (cudaMemcpy2DAsync) on `stream`.
+ * Used by the host-buffer pipeline to upload only the [pd|qd|soc] columns (33 of 57) of the reference's state rows
+ * (rpo/algo/rpo_ddpg.py:93,168: states live on the host between steps). */
+int rpo_copy_rows_h2d(float* dst_dev, int ld_dev, const float* src_host, int ld_host, int ncols, int64_t nrows, void* stream);
+int rpo_copy_rows_d2h(float* dst_host, int ld_host, const float* src_dev, int ld_dev, int ncols, int64_t nrows, void* stream);
+
 /* ------------------------------------------------------------------ measurement helpers ----------------------- */
 /* Dependency-free FP32 FMA micro-kernel used by bench.py to measure the FP32 roofline denominator on the box
  * (SURVEY.md §8d).  Launches `blocks` x `threads`, `iters` x 8 independent FMA chains x 4 per thread; out (blocks*threads) floats.

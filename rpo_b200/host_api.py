@@ -2,8 +2,12 @@
 
 The reference's callers hold numpy / CPU-torch batches (replay samples, rollout states — rpo_ddpg.py:93,165-174)
 and receive CPU arrays back (rpo_ddpg.py:108-109).  `HostProjector` takes pinned host buffers, streams them to the
-GPU in chunks on several CUDA streams (H2D copy, kernels and D2H copy of different chunks overlap), and writes the
-results into pinned host buffers.  Used by bench.py for the end-to-end (`e2e`) number.
+GPU in chunks on several CUDA streams (H2D copy, kernels and D2H copy of different chunks overlap on the two DMA
+engines and the SMs), and writes the results into pinned host buffers.  State rows cross PCIe whole (contiguous
+DMA): uploading only the 33 columns the path reads with a strided copy (rpo_copy_rows_h2d, 132 of every 228 bytes)
+was measured 3x SLOWER end to end (3.1e7 vs 9.9e7 projected actions/s) — the DMA engine handles it row by row.
+Pass `state_cols=33` only when the caller already holds a compact (B,33) [pd|qd|soc] matrix.
+Device staging buffers are allocated once per stream slot.  Used by bench.py for the end-to-end (`e2e`) number.
 """
 from __future__ import annotations
 
@@ -21,6 +25,9 @@ class HostProjector(object):
         self.chunk = int(chunk)
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(n_streams)]
         self.p = dict(lr=corr_lr, momentum=momentum, corr_eps=corr_eps, n_steps=n_steps, tol=tol, max_iters=max_iters)
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.slots = [dict(x=torch.empty(self.chunk * 57, **f32), z=torch.empty(self.chunk, 14, **f32),
+                           g=torch.empty(self.chunk, 43, **f32)) for _ in range(n_streams)]
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self.launches = 0
@@ -31,34 +38,42 @@ class HostProjector(object):
 
     def project_backward(self, state: torch.Tensor, z: torch.Tensor, dl_dy: Optional[torch.Tensor],
                          y_corr_out: torch.Tensor, dl_dz_out: Optional[torch.Tensor]):
-        """state (B,57|33), z (B,14), dl_dy (B,43) pinned CPU float32 -> y_corr_out (B,43), dl_dz_out (B,14) pinned CPU.
-        Completion + correction (+ GRG backward of the completion when dl_dy is given).  Blocks until results landed."""
+        """state (B, >=33) rows [pd|qd|soc|...], z (B,14), dl_dy (B,43): pinned CPU float32 ->
+        y_corr_out (B,43), dl_dz_out (B,14) pinned CPU.  Completion + correction (+ GRG backward of the completion
+        when dl_dy is given).  Blocks until the results have landed in host memory."""
         B = z.shape[0]
         p = self.p
+        cols = state.shape[1]
+        assert state.dtype == torch.float32 and state.is_contiguous() and 33 <= cols <= 57
         cur = torch.cuda.current_stream(self.device)
         for s in self.streams:
             s.wait_stream(cur)
         self.h2d_bytes = self.d2h_bytes = self.launches = 0
-        for i, b0 in enumerate(range(0, B, self.chunk)):
-            b1 = min(B, b0 + self.chunk)
-            s = self.streams[i % len(self.streams)]
-            with torch.cuda.stream(s):
-                d_state = state[b0:b1].to(self.device, non_blocking=True)
-                d_z = z[b0:b1].to(self.device, non_blocking=True)
-                self.h2d_bytes += (state[b0:b1].numel() + z[b0:b1].numel()) * 4
-                yc, y, _, _ = ops.evopf_project(d_state, d_z, p["lr"], p["momentum"], p["corr_eps"], p["n_steps"],
-                                                tol=p["tol"], max_iters=p["max_iters"], want_y=dl_dy is not None,
-                                                want_flags=False)
-                self.launches += 1
-                y_corr_out[b0:b1].copy_(yc, non_blocking=True)
-                self.d2h_bytes += yc.numel() * 4
-                if dl_dy is not None:
-                    d_g = dl_dy[b0:b1].to(self.device, non_blocking=True)
-                    self.h2d_bytes += d_g.numel() * 4
-                    dz, _ = ops.evopf_complete_bwd(y, d_g, need_dx=False)
+        with torch.cuda.device(self.device):
+            for i, b0 in enumerate(range(0, B, self.chunk)):
+                b1 = min(B, b0 + self.chunk)
+                n = b1 - b0
+                s = self.streams[i % len(self.streams)]
+                slot = self.slots[i % len(self.slots)]
+                with torch.cuda.stream(s):
+                    d_x, d_z = slot["x"][:n * cols].view(n, cols), slot["z"][:n]
+                    d_x.copy_(state[b0:b1], non_blocking=True)
+                    d_z.copy_(z[b0:b1], non_blocking=True)
+                    self.h2d_bytes += n * (cols + 14) * 4
+                    yc, y, _, _ = ops.evopf_project(d_x, d_z, p["lr"], p["momentum"], p["corr_eps"], p["n_steps"],
+                                                    tol=p["tol"], max_iters=p["max_iters"], want_y=dl_dy is not None,
+                                                    want_flags=False)
                     self.launches += 1
-                    dl_dz_out[b0:b1].copy_(dz, non_blocking=True)
-                    self.d2h_bytes += dz.numel() * 4
+                    y_corr_out[b0:b1].copy_(yc, non_blocking=True)
+                    self.d2h_bytes += yc.numel() * 4
+                    if dl_dy is not None:
+                        d_g = slot["g"][:n]
+                        d_g.copy_(dl_dy[b0:b1], non_blocking=True)
+                        self.h2d_bytes += d_g.numel() * 4
+                        dz, _ = ops.evopf_complete_bwd(y, d_g, need_dx=False)
+                        self.launches += 1
+                        dl_dz_out[b0:b1].copy_(dz, non_blocking=True)
+                        self.d2h_bytes += dz.numel() * 4
         for s in self.streams:
             cur.wait_stream(s)
         cur.synchronize()

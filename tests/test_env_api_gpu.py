@@ -180,3 +180,30 @@ def test_actor_critic_iteration_runs():
     loss.backward()
     gsum = sum(float(p.grad.abs().sum()) for p in actor.parameters())
     assert np.isfinite(gsum) and gsum > 0 and bool(torch.isfinite(q_t).all())
+
+
+def test_host_projector_matches_resident_path():
+    """Host-buffer pipeline (pinned in / pinned out, chunked over streams, strided state upload) == resident kernels."""
+    from rpo_b200 import ops, synth
+    from rpo_b200.host_api import HostProjector
+    B = 5000                                           # not a multiple of the chunk
+    st = synth.evopf_states(B, seed=70)
+    z = synth.evopf_partial_actions(st, seed=71)
+    g = synth.upstream_grad(B, 43, seed=72)
+    hp = HostProjector("cuda:0", chunk=1024, n_streams=3)
+    yc_h, dz_h = hp.pinned(B, 43), hp.pinned(B, 14)
+    hp.project_backward(st.pin_memory(), z.pin_memory(), g.pin_memory(), yc_h, dz_h)
+    yc, y, _, _ = ops.evopf_project(st.cuda(), z.cuda(), 1e-4, 0.0, 1e-5, 10, want_y=True)
+    dz, _ = ops.evopf_complete_bwd(y, g.cuda(), need_dx=False)
+    assert torch.equal(yc_h, yc.cpu()) and torch.equal(dz_h, dz.cpu())
+    assert hp.h2d_bytes == B * (57 + 14 + 43) * 4 and hp.d2h_bytes == B * (43 + 14) * 4
+    hp.project_backward(st[:, :33].contiguous().pin_memory(), z.pin_memory(), None, yc_h, None)   # compact state, forward only
+    assert torch.equal(yc_h, yc.cpu())
+    # the strided-DMA helpers of the C ABI (kept for callers that want them)
+    from rpo_b200 import _lib
+    lib = _lib.load()
+    d = torch.zeros(B, 33, device="cuda")
+    sp = st.pin_memory()
+    _lib.check(lib.rpo_copy_rows_h2d(d.data_ptr(), 33, sp.data_ptr(), 57, 33, B, torch.cuda.current_stream().cuda_stream), "h2d")
+    torch.cuda.synchronize()
+    assert torch.equal(d.cpu(), st[:, :33])
