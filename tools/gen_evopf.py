@@ -631,12 +631,38 @@ class Gen(object):
         return "\n".join(self.out) + "\n"
 
 
+def op_stats(txt):
+    """Static FP32 operation counts of the generated functions (FMA = 2 flop, mul/add = 1) and the executed-flop
+    model  F_exec(n_newton, K) = newton_iter * n_newton + corr_step * K + tail  used by bench.py / DESIGN.md."""
+    import json
+    import re
+    per = {}
+    for f in re.split(r"\nRPO_HD ", txt)[1:]:
+        name = re.match(r"\w+\s+(\w+)", f).group(1)
+        body = f[f.index("{"):]
+        small = body.count("SINCOS_SMALL(")
+        fma = body.count("FMA(") + 9 * small                      # rpo_sincosf_small: 9 FMA + 2 mul
+        mul = len(re.findall(r"[\w\]\)] \* [\w\(-]", body)) + body.count("*=") + 2 * small
+        add = len(re.findall(r"[\w\]\)] [+-] [\w\(]", body)) + body.count("+=") + body.count("-=")
+        per[name] = dict(fma=fma, mul=mul, add=add, flop=2 * fma + mul + add)
+    fl = lambda *names: sum(per[n]["flop"] for n in names)
+    newton = fl("evopf_eval_full", "evopf_newton_rhs", "evopf_factor", "evopf_solve", "evopf_newton_update")
+    post = fl("evopf_direction_post", "evopf_rhs_t", "evopf_solve_t", "evopf_colsums", "evopf_solve")
+    corr = fl("evopf_eval_full", "evopf_eq_resid", "evopf_ineq", "evopf_factor") + post + 2 * 43
+    bwd = fl("evopf_eval_full", "evopf_factor", "evopf_rhs_t", "evopf_solve_t", "evopf_colsums", "evopf_backward")
+    return dict(per_function=per, newton_iter_flop=newton, corr_step_flop=corr, tail_flop=fl("evopf_tail"),
+                backward_flop=bwd, note="general-path sincos not counted (small-angle path taken by the data)")
+
+
 def main():
     g = Gen()
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "rpo_b200", "csrc", "evopf_gen.cuh")
     txt = g.generate()
     with open(out, "w") as f:
         f.write(txt)
+    import json
+    with open(out.replace("evopf_gen.cuh", "evopf_gen_stats.json"), "w") as f:
+        json.dump(op_stats(txt), f, indent=1)
     print("order", g.order, "nnzY", g.nnz, "nL", g.nL, "nU", g.nU, "lu_ops", g.lu_ops, "lines", txt.count("\n"))
 
 
