@@ -1,0 +1,151 @@
+#!/usr/bin/env python
+"""Data-parallel RPO-DDPG on EVOPF-v0 with the B200 projection path (BASELINE.json configs[3]-style run).
+
+  python examples/train_evopf_dp.py                                   # 1 GPU
+  python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 examples/train_evopf_dp.py
+
+Every rank owns `--envs` EVOPF replicas stepped on the GPU (rpo_b200.vector) and a device-resident replay buffer;
+the projection (completion + correction, GRG backward) runs with NO communication; the only collective is ONE
+all-reduce of the flat actor / critic gradient bucket per optimiser step (rpo_b200.dist.FlatGradBucket).
+The update rules follow rpo/algo/rpo_ddpg.py:163-205,307-337 (critic smooth-L1 on the projected target action,
+actor loss -Q + nju . ineq_dist through complete_partial, soft target update, dual ascent on nju).
+This is a harness around the hot path, not a re-implementation of the reference's agent layer.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+import torch.nn as nn  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+from rpo_b200.algo import RPOProjectionMixin  # noqa: E402
+from rpo_b200.dist import FlatGradBucket, broadcast_parameters  # noqa: E402
+from rpo_b200.env import EVOPFEnv  # noqa: E402
+from rpo_b200.vector import DeviceReplay, EvopfVectorEnv  # noqa: E402
+
+
+class Projector(RPOProjectionMixin):
+    def __init__(self, env, a):
+        self.env = env
+        self.corr_lr = self.eval_lr = a.corr_lr
+        self.max_steps, self.eval_steps = a.max_steps, 50
+        self.corr_eps, self.corr_momentum, self.corr_mode = 1e-5, 0.0, 0
+        self.exact_loop_exit = False          # every shard takes max_steps steps: no host sync inside the training step
+
+
+def mlp(i, o, h=256, out_act=None):
+    layers = [nn.Linear(i, h), nn.ReLU(), nn.Linear(h, h), nn.ReLU(), nn.Linear(h, o)]
+    if out_act is not None:
+        layers.append(out_act)
+    return nn.Sequential(*layers)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--envs", type=int, default=4096)
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--iters", type=int, default=40)
+    ap.add_argument("--corr-lr", type=float, default=1e-4)
+    ap.add_argument("--max-steps", type=int, default=10)
+    ap.add_argument("--policy-fre", type=int, default=4)
+    a = ap.parse_args()
+    rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(1000 + rank)                      # different seeds: broadcast_parameters must equalise the replicas
+    env = EVOPFEnv(device=dev)
+    proj = Projector(env, a)
+    venv = EvopfVectorEnv(a.envs, dev, seed=rank)
+    actor, critic = mlp(57, 14, out_act=nn.Tanh()).to(dev), mlp(57 + 43, 1).to(dev)
+    actor_t, critic_t = mlp(57, 14, out_act=nn.Tanh()).to(dev), mlp(57 + 43, 1).to(dev)
+    nju = nn.Linear(58, 1, bias=False).to(dev)
+    nn.init.zeros_(nju.weight)
+    broadcast_parameters([actor, critic, nju])
+    actor_t.load_state_dict(actor.state_dict())
+    critic_t.load_state_dict(critic.state_dict())
+    b_critic = FlatGradBucket(critic.parameters())
+    b_actor = FlatGradBucket(list(actor.parameters()) + list(nju.parameters()))
+    opt_c = torch.optim.Adam(critic.parameters(), lr=3e-4)
+    opt_a = torch.optim.Adam(actor.parameters(), lr=1e-4)
+    opt_n = torch.optim.Adam(nju.parameters(), lr=2e-2, maximize=True)
+    replay = DeviceReplay(a.envs * 64, dev, state=57, action=43, next_state=57, reward=1, done=1)
+
+    def policy(net, s, noise=0.0):
+        lo, hi = env.update_device(s)                   # volatile box on the device (f-1)
+        u = net(s)
+        if noise:
+            u = (u + noise * torch.randn_like(u)).clamp(-1, 1)
+        return lo + (hi - lo) * 0.5 * (u + 1.0)
+
+    state = venv.reset()
+    n_proj = 0
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for it in range(a.iters):
+        with torch.no_grad():                           # rollout of all replicas (rpo_ddpg.py:96-118, vectorised)
+            act = proj.process_action(state, policy(actor, state, noise=0.1))
+            n_proj += a.envs
+            nxt, rew, done, _, _ = venv.step(act)
+            replay.extend(state=state, action=act, next_state=nxt, reward=rew, done=done.float())
+            state = nxt
+        smp = replay.sample(a.batch)
+        with torch.no_grad():                           # critic target (rpo_ddpg.py:327-332)
+            na = proj.process_action(smp["next_state"], policy(actor_t, smp["next_state"]))
+            n_proj += a.batch
+            tq = smp["reward"] + 0.95 * (1 - smp["done"]) * critic_t(torch.cat([smp["next_state"], na], 1))
+        b_critic.zero_()
+        F.smooth_l1_loss(critic(torch.cat([smp["state"], smp["action"]], 1)), tq).backward()
+        b_critic.all_reduce_mean()                      # the one collective of the critic step
+        opt_c.step()
+        if it % a.policy_fre == 0:                      # actor step (rpo_ddpg.py:184-205,307-324)
+            b_actor.zero_()
+            s = smp["state"]
+            act_c = env.complete_partial(s, policy(actor, s))          # autograd: GRG backward kernel
+            n_proj += a.batch
+            loss = (-critic(torch.cat([s, act_c], 1)) + nju(env.ineq_dist(s, act_c))).mean()
+            loss.backward()
+            b_actor.all_reduce_mean()
+            opt_a.step()
+            opt_n.step()
+            with torch.no_grad():
+                nju.weight.clamp_(min=0)
+                for t, o in ((actor_t, actor), (critic_t, critic)):
+                    for pt, po in zip(t.parameters(), o.parameters()):
+                        pt.lerp_(po, 0.005)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    # replicas must still be identical (same broadcast start + same averaged gradients)
+    w = torch.cat([p.detach().reshape(-1) for p in list(actor.parameters()) + list(critic.parameters())])
+    drift = torch.zeros(1, device=dev)
+    if world > 1:
+        w0 = w.clone()
+        dist.broadcast(w0, src=0)
+        drift = (w - w0).abs().max().view(1)
+        dist.all_reduce(drift, op=dist.ReduceOp.MAX)
+        tot = torch.tensor([float(n_proj)], device=dev)
+        dist.all_reduce(tot)
+        n_all = float(tot.item())
+    else:
+        n_all = float(n_proj)
+    if rank == 0:
+        print(json.dumps({"world": world, "iters": a.iters, "envs_per_gpu": a.envs, "batch_per_gpu": a.batch,
+                          "iters_per_s": a.iters / dt, "projected_actions_per_s": n_all / dt,
+                          "env_steps_per_s": world * a.envs * a.iters / dt, "max_replica_drift": float(drift.item()),
+                          "final_reward_mean": float(rew.mean()), "finite": bool(torch.isfinite(w).all())}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

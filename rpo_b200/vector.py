@@ -1,0 +1,115 @@
+"""Device-resident rollout plumbing for the "next" rows of SURVEY.md §8(f): vectorised EVOPF replicas stepped by
+the batched step kernel (f-2), a device-side replay ring buffer (f-2) and a device-side exogenous-row sampler (f-4).
+
+The reference rolls out ONE environment on the host (rpo_ddpg.py:88-118), pushes every transition through numpy
+(buffer.py:22-29) and re-uploads seven arrays per training step (rpo_ddpg.py:165-174).  Here N replicas live on the
+GPU: states, actions, rewards and the replay memory never leave HBM.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict
+
+import torch
+
+from . import evopf_constants as K
+from . import ops
+from .case14 import PD, QD, case14
+
+
+class EvopfExoSampler(object):
+    """Draws exogenous rows [pd(14) | qd(14) | price window(24)] on the device with the reference loaders' distributions
+    (data/demand.py:47-67, data/price.py:40-47): case share mixed with Dirichlet(1) over the 11 load buses (rho = .5),
+    total load following a daily curve, qd = pd tan(acos(U(.9,1))) sign(Qd), price = curve (1+N)(1+.1 N)/100."""
+
+    def __init__(self, device, seed: int = 0, T: int = 24):
+        self.device = torch.device(device)
+        self.T = T
+        self.gen = torch.Generator(device=self.device).manual_seed(seed)
+        bus = case14()["bus"]
+        pd_case = torch.tensor(bus[:, PD], dtype=torch.float64)
+        self.share = (pd_case / pd_case.sum()).to(self.device, torch.float32)
+        self.load_mask = (pd_case != 0).to(self.device)
+        self.q_sign = torch.tensor(bus[:, QD], dtype=torch.float64).sign().to(self.device, torch.float32)
+        self.total = float(pd_case.sum() / 100.0)                      # 2.59 pu
+        h = torch.arange(T, dtype=torch.float32)
+        self.demand_curve = (1.0 + 0.16 * torch.sin((h - 9.0) * 2 * math.pi / T)).to(self.device)
+        self.price_curve = (0.49 * (1.0 + 0.25 * torch.sin((h - 15.0) * 2 * math.pi / T))).to(self.device)
+
+    def _rand(self, *shape):
+        return torch.rand(*shape, generator=self.gen, device=self.device)
+
+    def _randn(self, *shape):
+        return torch.randn(*shape, generator=self.gen, device=self.device)
+
+    def rows(self, hour: torch.Tensor) -> torch.Tensor:
+        """hour (N,) int64 in [0, T) -> (N, 52) float32."""
+        n = hour.shape[0]
+        e = -torch.log(self._rand(n, 14).clamp_min(1e-12)) * self.load_mask        # Dirichlet(1) via normalised Exp(1)
+        dirich = e / e.sum(dim=1, keepdim=True)
+        ratio = 0.5 * self.share[None] + 0.5 * dirich
+        pd = ratio * (self.total * self.demand_curve[hour])[:, None]
+        pf = 0.9 + 0.1 * self._rand(n, 14)
+        qd = pd * torch.tan(torch.acos(pf)) * self.q_sign[None]
+        idx = (hour[:, None] + torch.arange(24, device=self.device)[None]) % self.T
+        ahead_valid = (hour[:, None] + torch.arange(24, device=self.device)[None]) < self.T
+        price = self.price_curve[idx] * (1 + self._randn(n, 24)) * (1 + 0.1 * self._randn(n, 1)) * ahead_valid
+        return torch.cat([pd, qd, price], dim=1).float()
+
+
+class EvopfVectorEnv(object):
+    """N independent EVOPF-v0 replicas on one GPU; `step` = one launch of rpo_evopf_step (evopf.py:348-366 row-wise).
+    Episodes last T = 24 steps (demand.py:69-75) and restart automatically (soc back to 0.2, evopf.py:62-63,243)."""
+
+    def __init__(self, n: int, device, seed: int = 0):
+        self.n, self.device = n, torch.device(device)
+        self.exo = EvopfExoSampler(self.device, seed)
+        self.T = self.exo.T
+        self.hour = torch.zeros(n, dtype=torch.int64, device=self.device)
+        self.state = None
+
+    def reset(self) -> torch.Tensor:
+        self.hour.zero_()
+        rows = self.exo.rows(self.hour)
+        soc = torch.full((self.n, 5), K.B_LOW + 0.1, device=self.device)
+        self.state = torch.cat([rows[:, :28], soc, rows[:, 28:]], dim=1).contiguous()
+        return self.state
+
+    def step(self, action: torch.Tensor):
+        """action (N,43) -> next_state (N,57), reward (N,), done (N,) bool, eq_viol (N,28), ineq_viol (N,58)."""
+        nxt_hour = self.hour + 1
+        done = nxt_hour >= self.T
+        rows = self.exo.rows(torch.where(done, torch.zeros_like(nxt_hour), nxt_hour))
+        ns, rew, eqv, iqv = ops.evopf_step(self.state, action, rows)
+        if bool(done.any()):
+            ns = ns.clone()
+            ns[done, 28:33] = K.B_LOW + 0.1
+        self.hour = torch.where(done, torch.zeros_like(nxt_hour), nxt_hour)
+        self.state = ns
+        return ns, rew, done, eqv, iqv
+
+
+class DeviceReplay(object):
+    """Ring buffer of transitions in HBM with uniform sampling on the device (reference: utils/buffer.py:3-34)."""
+
+    def __init__(self, capacity: int, device, **shapes: int):
+        self.capacity, self.device = int(capacity), torch.device(device)
+        self.buf: Dict[str, torch.Tensor] = {k: torch.zeros(self.capacity, d, device=self.device) for k, d in shapes.items()}
+        self.pointer = 0
+        self.size = 0
+        self.gen = torch.Generator(device=self.device).manual_seed(1234)
+
+    def __len__(self):
+        return self.size
+
+    def extend(self, **rows: torch.Tensor):
+        n = next(iter(rows.values())).shape[0]
+        idx = (self.pointer + torch.arange(n, device=self.device)) % self.capacity
+        for k, v in rows.items():
+            self.buf[k][idx] = v.view(n, -1).to(self.buf[k].dtype)
+        self.pointer = (self.pointer + n) % self.capacity
+        self.size = min(self.size + n, self.capacity)
+
+    def sample(self, num: int) -> Dict[str, torch.Tensor]:
+        idx = torch.randint(0, self.size, (num,), generator=self.gen, device=self.device)
+        return {k: v[idx] for k, v in self.buf.items()}

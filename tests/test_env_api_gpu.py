@@ -207,3 +207,26 @@ def test_host_projector_matches_resident_path():
     _lib.check(lib.rpo_copy_rows_h2d(d.data_ptr(), 33, sp.data_ptr(), 57, 33, B, torch.cuda.current_stream().cuda_stream), "h2d")
     torch.cuda.synchronize()
     assert torch.equal(d.cpu(), st[:, :33])
+
+
+def test_vector_env_and_replay():
+    """f-2 / f-4: N replicas stepped by the batched step kernel, device replay, device exogenous sampler."""
+    from rpo_b200 import ops, synth
+    from rpo_b200.vector import DeviceReplay, EvopfVectorEnv
+    env = EvopfVectorEnv(512, "cuda:0", seed=3)
+    s = env.reset()
+    assert s.shape == (512, 57) and float(s[:, 0].abs().max()) == 0.0 and bool((s[:, 28:33] == 0.2).all())
+    assert 2.0 < float(s[:, :14].sum(1).mean()) < 3.2
+    rb = DeviceReplay(2048, "cuda:0", state=57, action=43, next_state=57, reward=1, done=1)
+    for t in range(30):
+        z = synth.evopf_partial_actions(s, seed=t)
+        a, _, _, _ = ops.evopf_project(s, z, 1e-4, 0.0, 1e-5, 10)
+        ns, r, done, eqv, iqv = env.step(a)
+        rb.extend(state=s, action=a, next_state=ns, reward=r, done=done.float())
+        assert bool(done.all()) == (t % 24 == 23)
+        if t % 24 == 23:
+            assert bool((ns[:, 28:33] == 0.2).all())
+        s = ns
+    assert len(rb) == 2048
+    b = rb.sample(256)
+    assert b["state"].shape == (256, 57) and b["reward"].shape == (256, 1) and bool(torch.isfinite(b["reward"]).all())
