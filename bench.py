@@ -192,6 +192,13 @@ def main():
     import torch.distributed as dist
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        # NCCL builds its communicator lazily at the first collective (hundreds of ms with the GPU idle): do it here,
+        # not at the barrier that opens the timed region — the idle GPU would drop its clocks and the first ~50 ms of
+        # the timed region would measure the ramp (seen as 0.43 ms instead of 0.15 ms on the backward kernel).
+        warm = torch.zeros(1, device=dev)
+        dist.all_reduce(warm)
+        dist.barrier()
+        torch.cuda.synchronize()
 
     B = 1 << args.log2_batch
     # each rank owns its own contiguous shard of the global batch (seeded per rank); no data-path collective
@@ -242,6 +249,7 @@ def main():
         dz, _ = ops.evopf_complete_bwd(y, g, need_dx=False)
         ev[3 * i + 2].record()
         ev[3 * i + 3].record()
+    t_enqueue = time.perf_counter() - t_wall
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -251,8 +259,9 @@ def main():
     proj_ms = sum(ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(args.steps)) / args.steps
     bwd_ms = sum(ev[3 * i + 1].elapsed_time(ev[3 * i + 2]) for i in range(args.steps)) / args.steps
     if os.environ.get("RPO_BENCH_DEBUG"):
-        print("[rank %d] total %.3f ms  project %.3f  bwd %.3f  wall %.3f ms/step" %
-              (rank, total_ms / args.steps, proj_ms, bwd_ms, t_wall / args.steps * 1e3), file=sys.stderr, flush=True)
+        print("[rank %d] total %.3f ms  project %.3f  bwd %.3f  wall %.3f ms/step  host enqueue %.3f ms/step" %
+              (rank, total_ms / args.steps, proj_ms, bwd_ms, t_wall / args.steps * 1e3, t_enqueue / args.steps * 1e3),
+              file=sys.stderr, flush=True)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
