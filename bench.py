@@ -214,17 +214,26 @@ def main():
         dz, _ = ops.evopf_complete_bwd(y, g, need_dx=False)
         return yc, y, flags, dz
 
-    # untimed clock ramp: an idle B200 sits at 120 MHz and needs a few hundred ms of load to reach its boost clock;
-    # without it a short timed region (K x 1.6 ms) measures the ramp, not the kernel (seen as +20 % and 2x on the
-    # latency-sensitive backward kernel).  The W warm-up steps requested on the command line follow.
+    # one step (memset + k_evopf_project + k_evopf_bwd) captured in a CUDA graph: the timed region replays it K times,
+    # so host-side jitter (8 ranks sharing one host) cannot starve the GPU between 1.4 ms kernels
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            out = step()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = step()
+    # untimed clock ramp: an idle B200 sits at 120 MHz and needs a few hundred ms of load to reach steady clocks
+    # (SM and memory side); a short timed region (K x 1.6 ms) would otherwise measure the ramp, not the kernels
+    # (seen as +20 % and 3x on the latency-sensitive backward kernel).
     t_ramp = time.perf_counter()
     while time.perf_counter() - t_ramp < 1.0:
         for _ in range(20):
-            out = step()
+            graph.replay()
         torch.cuda.synchronize()
-    for _ in range(args.warmup):
-        out = step()
-    torch.cuda.synchronize()
     # workload facts for the roofline: mean Newton iterations, steps the reference's loop test would take
     _, status = ops.evopf_complete_fwd(st, z, return_status=True)
     n_newton = float((status & 0xff).float().mean())
@@ -234,14 +243,33 @@ def main():
     assert not_converged <= max(4, B // 100000), "too many non-converged instances: %d" % not_converged
 
     sampler = ClockSampler(local_rank)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # ranks are aligned by the barrier BEFORE the W warm-up steps: the GPUs idle while waiting at a barrier, and the
+    # warm-up steps then bring them back to steady state before the first timed step
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        graph.replay()
     sampler.start()
     t_wall = time.perf_counter()
-    ev[0].record()
+    ev0.record()
     for i in range(args.steps):
+        graph.replay()
+    ev1.record()
+    t_enqueue = time.perf_counter() - t_wall
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall = time.perf_counter() - t_wall
+    clocks = sampler.stop()
+    total_ms = ev0.elapsed_time(ev1)
+    # per-kernel durations: instrumented pass of the same step right after the timed region (CUDA events around each
+    # launch on the launching stream; a captured graph cannot carry timing events)
+    n_ins = max(3, min(args.steps, 50))
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * n_ins + 1)]
+    ev[0].record()
+    for i in range(n_ins):
         yc, y, flags, status2 = ops.evopf_project(st, z, CORR["lr"], CORR["momentum"], CORR["corr_eps"], CORR["n_steps"],
                                                   tol=NEWTON["tol"], max_iters=NEWTON["max_iters"], want_y=True,
                                                   want_flags=True)
@@ -249,17 +277,11 @@ def main():
         dz, _ = ops.evopf_complete_bwd(y, g, need_dx=False)
         ev[3 * i + 2].record()
         ev[3 * i + 3].record()
-    t_enqueue = time.perf_counter() - t_wall
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t_wall = time.perf_counter() - t_wall
-    clocks = sampler.stop()
-    total_ms = ev[0].elapsed_time(ev[3 * args.steps])
-    proj_ms = sum(ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(args.steps)) / args.steps
-    bwd_ms = sum(ev[3 * i + 1].elapsed_time(ev[3 * i + 2]) for i in range(args.steps)) / args.steps
+    proj_ms = sorted(ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(n_ins))[n_ins // 2]
+    bwd_ms = sorted(ev[3 * i + 1].elapsed_time(ev[3 * i + 2]) for i in range(n_ins))[n_ins // 2]
     if os.environ.get("RPO_BENCH_DEBUG"):
-        print("[rank %d] total %.3f ms  project %.3f  bwd %.3f  wall %.3f ms/step  host enqueue %.3f ms/step" %
+        print("[rank %d] total %.3f ms/step  project %.3f  bwd %.3f  wall %.3f ms/step  host enqueue %.3f ms/step" %
               (rank, total_ms / args.steps, proj_ms, bwd_ms, t_wall / args.steps * 1e3, t_enqueue / args.steps * 1e3),
               file=sys.stderr, flush=True)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -340,6 +362,8 @@ def main():
         "peak_source": "rpo_fp32_peak_probe measured in this run (dependency-free FFMA micro-kernel)",
         "algorithmic_flops_per_instance": f_proj, "mean_newton_iters": n_newton, "correction_steps": CORR["n_steps"],
         "kernel_ms": proj_ms, "bwd_kernel_ms": bwd_ms, "executed": executed,
+        "kernel_ms_source": "median over an instrumented pass (CUDA events around each launch) right after the timed "
+                            "region; the timed region replays a CUDA graph of the step (memset + 2 kernels)",
         "whole_step": {"achieved": B * (f_proj + FLOPS_BWD) / ((proj_ms + bwd_ms) * 1e-3) / 1e12,
                        "frac": B * (f_proj + FLOPS_BWD) / ((proj_ms + bwd_ms) * 1e-3) / 1e12 / fp32_peak},
         "hbm": {"achieved": value / world * BYTES_PER_ACTION / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -363,7 +387,8 @@ def main():
                    "instances_per_gpu": B, "input_dist": "D1 (uniform in the state-dependent partial box)",
                    "newton": NEWTON, "correction": CORR, "reference_loop_steps": k_ref, "non_converged_instances": not_converged,
                    "l2": "inputs larger than L2 (state %d MB + z %d MB per step)" % (B * 57 * 4 >> 20, B * 14 * 4 >> 20),
-                   "parallelism": "instance shards, no collective"},
+                   "parallelism": "instance shards, no collective",
+                   "timed_region": "K replays of a CUDA graph of one step, CUDA events at both ends, max over ranks"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * args.steps * world,
         "roofline": roofline, "cpu_baseline": cpu_baseline, "wall_s_timed_region": t_wall,
     }
