@@ -56,11 +56,30 @@ class RpoLibraryError(RuntimeError):
     pass
 
 
+def _try_build():
+    """The .so is a build artefact (git-ignored).  If it is missing but the CUDA toolchain is present, compile it for
+    sm_100a exactly as __graft_entry__.build() does.  This is a build step, not a fallback: without nvcc we still raise."""
+    import shutil
+    import subprocess
+    nvcc = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    src = os.path.join(_HERE, "csrc", "rpo_kernels.cu")
+    if not (os.path.isfile(nvcc) and os.path.isfile(src)):
+        return
+    cmd = [nvcc, "-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-gencode", "arch=compute_100a,code=sm_100a",
+           "-Xcompiler", "-fPIC", "-DRPO_BUILD_ARCH=\"sm_100a\"", "-shared", "-o", LIB_PATH, src, "-lcudart"]
+    try:
+        subprocess.check_call(cmd)
+    except Exception:
+        pass
+
+
 def load():
     """Load the shared library (once) and bind every symbol of the header; raises if anything is missing."""
     global _lib
     if _lib is not None:
         return _lib
+    if not os.path.isfile(LIB_PATH) and not os.environ.get("RPO_B200_LIB") and not os.environ.get("RPO_B200_NO_AUTOBUILD"):
+        _try_build()
     if not os.path.isfile(LIB_PATH):
         raise RpoLibraryError(
             "%s not found: the CUDA extension is not built (run __graft_entry__.build() or make -C rpo_b200/csrc). "
