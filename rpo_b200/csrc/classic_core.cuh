@@ -27,8 +27,8 @@ RPO_HD CartK cart_constants(int partial_idx) {
     k.C[1] = RC(0x1.bb67aep-1);   // cos(-pi/6)
     k.p = partial_idx;
     k.o = 1 - partial_idx;
-    k.inv_o = RC(1.0) / k.E[k.o];
-    k.ep = k.E[k.p];
+    k.inv_o = RC(1.0) / (partial_idx == 0 ? k.E[1] : k.E[0]);
+    k.ep = partial_idx == 0 ? k.E[0] : k.E[1];
     const real m = k.inv_o * k.ep;
     // A[:, p] - A[:, o] * (inv_o * ep)
     const real A0[6] = {k.C[0], -k.C[0], RC(1.0), RC(-1.0), RC(0.0), RC(0.0)};
@@ -41,21 +41,29 @@ RPO_HD CartK cart_constants(int partial_idx) {
     return k;
 }
 
+// NOTE: the action is indexed with selects, never with a run-time subscript (a[k.p] would force the 2-element array
+// into local memory and every loop iteration through the LSU: measured 3x slower).
+RPO_HD real cart_sel(bool first, real x, real y) { return first ? x : y; }
+
 // complete_partial (:369-373): a_p = z, a_o = (0 - z*E_p) * inv(E_o)
 RPO_HD void cart_complete(const CartK& k, real z, real* a) {
-    a[k.p] = z;
-    a[k.o] = (RC(0.0) - z * k.ep) * k.inv_o;
+    const real ao = (RC(0.0) - z * k.ep) * k.inv_o;
+    a[0] = cart_sel(k.p == 0, z, ao);
+    a[1] = cart_sel(k.p == 0, ao, z);
 }
 
 // autograd of complete_partial
-RPO_HD real cart_complete_bwd(const CartK& k, const real* da) { return da[k.p] + (da[k.o] * k.inv_o) * (-k.ep); }
+RPO_HD real cart_complete_bwd(const CartK& k, const real* da) {
+    const real dp = cart_sel(k.p == 0, da[0], da[1]), dn = cart_sel(k.p == 0, da[1], da[0]);
+    return dp + (dn * k.inv_o) * (-k.ep);
+}
 
 // eq_resid (:375-376) and ineq_resid (:378-379); returns the loop test max(|eq|, relu(ineq)) pieces
 RPO_HD void cart_resid(const CartK& k, const real* a, real* eq, real* ineq) {
-    *eq = RC(0.0) - (a[0] * k.E[0] + a[1] * k.E[1]);
-    const real ca = a[0] * k.C[0] + a[1] * k.C[1];
+    *eq = RC(0.0) - FMA(a[0], k.E[0], a[1] * k.E[1]);
+    const real ca = FMA(a[0], k.C[0], a[1] * k.C[1]);
     ineq[0] = ca - RC(8.0);
-    ineq[1] = (a[0] * (-k.C[0]) + a[1] * (-k.C[1])) - RC(8.0);
+    ineq[1] = -ca - RC(8.0);          // row 1 of A is -row 0 (cartpole.py:135)
     ineq[2] = a[0] - RC(10.0);
     ineq[3] = -a[0] - RC(10.0);
     ineq[4] = a[1] - RC(10.0);
@@ -65,13 +73,15 @@ RPO_HD void cart_resid(const CartK& k, const real* a, real* eq, real* ineq) {
 // ineq_partial_grad (:396-408)
 RPO_HD void cart_direction(const CartK& k, const real* a, real* out) {
     const real b[6] = {RC(8.0), RC(8.0), RC(10.0), RC(10.0), RC(10.0), RC(10.0)};
+    const real ap = cart_sel(k.p == 0, a[0], a[1]);
     real g = RC(0.0);
     for (int r = 0; r < 6; ++r) {
-        const real bm = a[k.p] * k.Ared[r] - b[r];
-        g += (bm > RC(0.0) ? RC(1.0) : RC(0.0)) * k.Ared[r];
+        const real bm = FMA(ap, k.Ared[r], -b[r]);
+        g += (bm > RC(0.0) ? k.Ared[r] : RC(0.0));
     }
-    out[k.p] = g;
-    out[k.o] = -(g * k.ep) * k.inv_o;
+    const real go = -(g * k.ep) * k.inv_o;
+    out[0] = cart_sel(k.p == 0, g, go);
+    out[1] = cart_sel(k.p == 0, go, g);
 }
 
 template <bool MOMENTUM>
@@ -144,15 +154,15 @@ RPO_HD void pen_complete(const PenEq& e, real z, real* a) {
 RPO_HD real pen_complete_bwd(const PenEq& e, const real* da) { return da[0] + (da[1] * e.inv) * (-e.ep); }
 
 RPO_HD void pen_resid(const PenEq& e, const real* a, real* eq, real* ineq) {
-    *eq = e.bias - (a[0] * e.ep + a[1] * e.eo);
-    *ineq = (a[0] * a[0] + a[1] * a[1]) - RC(32.0);
+    *eq = e.bias - FMA(a[0], e.ep, a[1] * e.eo);
+    *ineq = FMA(a[0], a[0], a[1] * a[1]) - RC(32.0);
 }
 
 RPO_HD void pen_direction(const PenEq& e, const real* a, real* out) {
     const real D0 = RC(2.0) * a[0], D1 = RC(2.0) * a[1];
-    const real dgp = D0 - D1 * (e.inv * e.ep);
-    const real bgp = RC(32.0) - (e.bias * e.inv) * D1;
-    const real bm = a[0] * dgp - bgp;
+    const real dgp = FMA(-D1, e.inv * e.ep, D0);
+    const real bgp = FMA(-(e.bias * e.inv), D1, RC(32.0));
+    const real bm = FMA(a[0], dgp, -bgp);
     const real g = (bm > RC(0.0) ? RC(1.0) : RC(0.0)) * dgp;
     out[0] = g;
     out[1] = -(g * e.ep) * e.inv;
