@@ -46,6 +46,21 @@ RPO_HD int evopf_complete(const real* x, const real* z, real* y, real tol, int m
     return st;
 }
 
+// action_step = lr*dir + momentum*prev;  y -= action_step  (rpo_ddpg.py:280-283).  Without momentum this is one FMA per
+// component (the reference rounds lr*dir before subtracting: <= 0.5 ulp of y apart).
+template <bool MOMENTUM>
+RPO_HD void evopf_apply_step(real* y, const real* dir, real* prev, real lr, real momentum) {
+    for (int i = 0; i < 43; ++i) {
+        if (MOMENTUM) {
+            const real s = FMA(momentum, prev[i], lr * dir[i]);
+            prev[i] = s;
+            y[i] = y[i] - s;
+        } else {
+            y[i] = FMA(-lr, dir[i], y[i]);
+        }
+    }
+}
+
 // One step of the post-correction loop body (rpo_ddpg.py:274,280-283) for corr_mode == 0:
 //   dir = ineq_partial_grad(state, y);  step = lr*dir + momentum*prev;  y -= step;  prev = step.
 // Returns whether this instance fails the loop test *before* the step (|eq_resid| or ineq_dist above eps).
@@ -54,14 +69,7 @@ RPO_HD bool evopf_correct_step(const real* x, const real* pe_max, const real* pe
                                real momentum, real corr_eps, real* minpiv) {
     real dir[43], eqmax, ineqmax;
     *minpiv = evopf_direction(x, pe_max, pe_min, y, dir, &eqmax, &ineqmax);
-    for (int i = 0; i < 43; ++i) {
-        real s = lr * dir[i];
-        if (MOMENTUM) {
-            s = s + momentum * prev[i];
-            prev[i] = s;
-        }
-        y[i] = y[i] - s;
-    }
+    evopf_apply_step<MOMENTUM>(y, dir, prev, lr, momentum);
     return (eqmax > corr_eps) || (ineqmax > corr_eps);
 }
 
@@ -123,14 +131,7 @@ RPO_HD void evopf_project_loop(const real* x, const real* z, real* y, real* scra
         } else {
             real dir[43];
             evopf_direction_post(y, pt, lu, ipiv, d, dir);
-            for (int i = 0; i < 43; ++i) {
-                real s = lr * dir[i];
-                if (MOMENTUM) {
-                    s = s + momentum * prev[i];
-                    prev[i] = s;
-                }
-                y[i] = y[i] - s;
-            }
+            evopf_apply_step<MOMENTUM>(y, dir, prev, lr, momentum);
             on_flag(k, (eqmax > corr_eps) || (ineqmax > corr_eps));
             if (++k >= n_steps) break;
         }
