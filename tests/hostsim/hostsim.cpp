@@ -79,5 +79,88 @@ void hs_evopf_project(const real* state, int ld, const real* z, real* y, real* y
     }
 }
 
+// ---- env steps and the classic-control environments (same per-instance code as the kernels) -------------------
+void hs_evopf_step(const real* state, const real* y, const real* exo, real* ns, real* reward, real* eqv, real* iqv, int B) {
+    for (int b = 0; b < B; ++b) {
+        const real* s = state + (long)b * 57;
+        const real* yy = y + (long)b * 43;
+        evopf_step_dyn(s, yy, exo + (long)b * 52, ns + (long)b * 57, reward + b);
+        if (eqv) {
+            EvopfPt pt;
+            evopf_eval_flows(yy, pt);
+            evopf_eq_resid(s, yy, pt, eqv + (long)b * 28);
+        }
+        if (iqv) {
+            real pe_max[5], pe_min[5];
+            evopf_pe_bounds(s + 28, pe_max, pe_min);
+            evopf_ineq(pe_max, pe_min, yy, iqv + (long)b * 58, (real*)0);
+            for (int i = 0; i < 58; ++i) iqv[(long)b * 58 + i] = FMAX(iqv[(long)b * 58 + i], RC(0.0));
+        }
+    }
+}
+
+void hs_cart_complete(const real* z, real* a, int B, int p) {
+    const CartK k = cart_constants(p);
+    for (int b = 0; b < B; ++b) cart_complete(k, z[b], a + 2 * (long)b);
+}
+void hs_cart_complete_bwd(const real* da, real* dz, int B, int p) {
+    const CartK k = cart_constants(p);
+    for (int b = 0; b < B; ++b) dz[b] = cart_complete_bwd(k, da + 2 * (long)b);
+}
+void hs_cart_direction(const real* a, real* out, int B, int p) {
+    const CartK k = cart_constants(p);
+    for (int b = 0; b < B; ++b) cart_direction(k, a + 2 * (long)b, out + 2 * (long)b);
+}
+void hs_cart_correct(real* a, int B, int p, real lr, real momentum, real eps, int n_steps, int* flags) {
+    const CartK k = cart_constants(p);
+    for (int b = 0; b < B; ++b) {
+        real prev[2] = {0, 0};
+        for (int s = 0; s < n_steps; ++s)
+            if (cart_correct_step<true>(k, a + 2 * (long)b, prev, lr, momentum, eps) && flags) flags[s] = 1;
+    }
+}
+void hs_cart_resid(const real* a, real* eq, real* ineq, int B) {
+    const CartK k = cart_constants(0);
+    for (int b = 0; b < B; ++b) {
+        real e, iq[6];
+        cart_resid(k, a + 2 * (long)b, &e, iq);
+        if (eq) eq[b] = e;
+        if (ineq) for (int r = 0; r < 6; ++r) ineq[(long)b * 6 + r] = iq[r];
+    }
+}
+void hs_cart_step(const real* s, const real* a, real* ns, int* done, int B) {
+    for (int b = 0; b < B; ++b) done[b] = cart_step(s + 6 * (long)b, a + 2 * (long)b, ns + 6 * (long)b);
+}
+
+void hs_pen_complete(const real* obs, const real* z, real* a, int B) {
+    for (int b = 0; b < B; ++b) pen_complete(pen_set_eq(obs + 5 * (long)b), z[b], a + 2 * (long)b);
+}
+void hs_pen_complete_bwd(const real* obs, const real* da, real* dz, int B) {
+    for (int b = 0; b < B; ++b) dz[b] = pen_complete_bwd(pen_set_eq(obs + 5 * (long)b), da + 2 * (long)b);
+}
+void hs_pen_direction(const real* obs, const real* a, real* out, int B) {
+    for (int b = 0; b < B; ++b) pen_direction(pen_set_eq(obs + 5 * (long)b), a + 2 * (long)b, out + 2 * (long)b);
+}
+void hs_pen_correct(const real* obs, real* a, int B, real lr, real momentum, real eps, int n_steps, int* flags) {
+    for (int b = 0; b < B; ++b) {
+        const PenEq e = pen_set_eq(obs + 5 * (long)b);
+        real prev[2] = {0, 0};
+        for (int s = 0; s < n_steps; ++s)
+            if (pen_correct_step<true>(e, a + 2 * (long)b, prev, lr, momentum, eps) && flags) flags[s] = 1;
+    }
+}
+void hs_pen_resid(const real* obs, const real* a, real* eq, real* ineq, int B) {
+    for (int b = 0; b < B; ++b) {
+        real e, q;
+        pen_resid(pen_set_eq(obs + 5 * (long)b), a + 2 * (long)b, &e, &q);
+        if (eq) eq[b] = e;
+        if (ineq) ineq[b] = q;
+    }
+}
+void hs_pen_step(const real* st, const real* a, real* nst, real* nobs, real* reward, int* done, int B) {
+    for (int b = 0; b < B; ++b)
+        done[b] = pen_step(st + 4 * (long)b, a + 2 * (long)b, nst + 4 * (long)b, nobs + 5 * (long)b, reward + b);
+}
+
 int hs_sizeof_real() { return (int)sizeof(real); }
 }

@@ -87,3 +87,19 @@ def test_rows_helper_accepts_strided_views():
         with pytest.raises(Exception):
             ops._rows(torch.zeros(4, 57), "state", 28)
         return
+
+
+def test_generated_header_is_up_to_date(tmp_path):
+    """tools/gen_evopf.py is deterministic and the committed rpo_b200/csrc/evopf_gen.cuh is its current output."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_evopf", os.path.join(root, "tools", "gen_evopf.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = mod.Gen()
+    txt = g.generate()
+    assert txt == open(os.path.join(root, "rpo_b200", "csrc", "evopf_gen.cuh")).read()
+    assert g.order == [7, 2, 10, 9, 11, 12, 13, 1, 4, 5, 3, 6, 8] and g.n == 22 and g.nL == 70 and g.nU == 92
+    st = mod.op_stats(txt)
+    assert 1500 < st["newton_iter_flop"] < 3000 and 2000 < st["corr_step_flop"] < 4000
