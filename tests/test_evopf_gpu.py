@@ -128,3 +128,38 @@ def test_golden_setpoint():
     assert rel_err(d.cpu(), torch.tensor(g["dir"])).max() <= GRAD_RTOL
     yc, _ = ops.evopf_correct(st, torch.tensor(g["y"]).cuda(), 1e-4, 0.0, 1e-5, 10)
     assert rel_err(yc.cpu(), torch.tensor(g["y_corr"])).max() <= Y_RTOL
+
+
+def test_unaligned_views_take_the_fallback_path():
+    """Pointers that are only 4-byte aligned (views into larger buffers) must not reach the TMA / float4 paths."""
+    import ctypes
+    from rpo_b200 import _lib, ops
+    lib = _lib.load()
+    B = 700
+    st, z = _inputs(B, "D1", seed=44)
+    st_d, z_d = st.cuda(), z.cuda()
+    y_ref = ops.evopf_complete_fwd(st_d, z_d)
+    # inputs and outputs placed at a 4-byte offset inside bigger allocations
+    big_s = torch.zeros(B * 57 + 1, device="cuda"); big_s[1:] = st_d.reshape(-1)
+    big_z = torch.zeros(B * 14 + 1, device="cuda"); big_z[1:] = z_d.reshape(-1)
+    big_y = torch.zeros(B * 43 + 1, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    rc = lib.rpo_evopf_complete_fwd(big_s.data_ptr() + 4, 57, big_z.data_ptr() + 4, big_y.data_ptr() + 4, B, 1e-5, 50, None, s)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert torch.equal(big_y[1:].view(B, 43), y_ref)
+    g = torch.randn(B, 43, device="cuda")
+    big_g = torch.zeros(B * 43 + 1, device="cuda"); big_g[1:] = g.reshape(-1)
+    big_dz = torch.zeros(B * 14 + 1, device="cuda")
+    rc = lib.rpo_evopf_complete_bwd(big_y.data_ptr() + 4, big_g.data_ptr() + 4, big_dz.data_ptr() + 4, None, B, s)
+    assert rc == 0
+    torch.cuda.synchronize()
+    dz_ref, _ = ops.evopf_complete_bwd(y_ref, g, need_dx=False)
+    assert torch.equal(big_dz[1:].view(B, 14), dz_ref)
+    big_yc = torch.zeros(B * 43 + 1, device="cuda")
+    rc = lib.rpo_evopf_project(big_s.data_ptr() + 4, 57, big_z.data_ptr() + 4, None, big_yc.data_ptr() + 4, B, 1e-5, 50,
+                               1e-4, 0.0, 1e-5, 10, None, None, s)
+    assert rc == 0
+    torch.cuda.synchronize()
+    yc_ref, _, _, _ = ops.evopf_project(st_d, z_d, 1e-4, 0.0, 1e-5, 10)
+    assert torch.equal(big_yc[1:].view(B, 43), yc_ref)
