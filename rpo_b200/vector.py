@@ -113,3 +113,40 @@ class DeviceReplay(object):
     def sample(self, num: int) -> Dict[str, torch.Tensor]:
         idx = torch.randint(0, self.size, (num,), generator=self.gen, device=self.device)
         return {k: v[idx] for k, v in self.buf.items()}
+
+
+@torch.no_grad()
+def evaluate_batched(venv: EvopfVectorEnv, policy, projector, max_len: int = 500):
+    """Batched counterpart of RPODDPG.eval (rpo_ddpg.py:207-264, SURVEY f-4): the reference plays 10 episodes one
+    after the other with B = 1 projections (eval_steps = 50 correction steps each); here all replicas of `venv` play
+    one episode in lock-step, every step being ONE fused projection launch with train=False semantics.
+
+    policy(state) -> partial action (N,14); projector.process_action(state, z, train=False) -> (action, steps).
+    Returns the reference's ten statistics: mean/std of episode reward, of the per-episode running mean of the max
+    inequality / equality violation, and of the per-episode maxima."""
+    state = venv.reset()
+    n = venv.n
+    dev = state.device
+    total = torch.zeros(n, device=dev)
+    mean_ineq = torch.zeros(n, device=dev)
+    mean_eq = torch.zeros(n, device=dev)
+    max_ineq = torch.zeros(n, device=dev)
+    max_eq = torch.zeros(n, device=dev)
+    alive = torch.ones(n, dtype=torch.bool, device=dev)
+    for i in range(max_len):
+        action, _ = projector.process_action(state, policy(state), train=False)
+        state, rew, done, eqv, iqv = venv.step(action)
+        iq, eq = iqv.max(dim=1).values, eqv.abs().max(dim=1).values
+        w = alive.float()
+        total += w * rew
+        mean_ineq += w * (iq - mean_ineq) / (i + 1)
+        mean_eq += w * (eq - mean_eq) / (i + 1)
+        max_ineq = torch.where(alive, torch.maximum(max_ineq, iq), max_ineq)
+        max_eq = torch.where(alive, torch.maximum(max_eq, eq), max_eq)
+        alive = alive & ~done
+        if not bool(alive.any()):
+            break
+    out = []
+    for v in (total, mean_ineq, mean_eq, max_ineq, max_eq):
+        out += [float(v.mean()), float(v.std(unbiased=False))]
+    return tuple(out)
