@@ -57,6 +57,7 @@ def main():
     ap.add_argument("--corr-lr", type=float, default=1e-4)
     ap.add_argument("--max-steps", type=int, default=10)
     ap.add_argument("--policy-fre", type=int, default=4)
+    ap.add_argument("--graph", action="store_true", help="capture the training iteration in CUDA graphs (SURVEY f-3)")
     a = ap.parse_args()
     rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(local)
@@ -66,7 +67,7 @@ def main():
     torch.manual_seed(1000 + rank)                      # different seeds: broadcast_parameters must equalise the replicas
     env = EVOPFEnv(device=dev)
     proj = Projector(env, a)
-    venv = EvopfVectorEnv(a.envs, dev, seed=rank)
+    venv = EvopfVectorEnv(a.envs, dev, seed=rank, default_generator=a.graph)
     actor, critic = mlp(57, 14, out_act=nn.Tanh()).to(dev), mlp(57 + 43, 1).to(dev)
     actor_t, critic_t = mlp(57, 14, out_act=nn.Tanh()).to(dev), mlp(57 + 43, 1).to(dev)
     nju = nn.Linear(58, 1, bias=False).to(dev)
@@ -76,10 +77,10 @@ def main():
     critic_t.load_state_dict(critic.state_dict())
     b_critic = FlatGradBucket(critic.parameters())
     b_actor = FlatGradBucket(list(actor.parameters()) + list(nju.parameters()))
-    opt_c = torch.optim.Adam(critic.parameters(), lr=3e-4)
-    opt_a = torch.optim.Adam(actor.parameters(), lr=1e-4)
-    opt_n = torch.optim.Adam(nju.parameters(), lr=2e-2, maximize=True)
-    replay = DeviceReplay(a.envs * 64, dev, state=57, action=43, next_state=57, reward=1, done=1)
+    opt_c = torch.optim.Adam(critic.parameters(), lr=3e-4, capturable=a.graph)
+    opt_a = torch.optim.Adam(actor.parameters(), lr=1e-4, capturable=a.graph)
+    opt_n = torch.optim.Adam(nju.parameters(), lr=2e-2, maximize=True, capturable=a.graph)
+    replay = DeviceReplay(a.envs * 64, dev, default_generator=a.graph, state=57, action=43, next_state=57, reward=1, done=1)
 
     def policy(net, s, noise=0.0):
         lo, hi = env.update_device(s)                   # volatile box on the device (f-1)
@@ -88,41 +89,89 @@ def main():
             u = (u + noise * torch.randn_like(u)).clamp(-1, 1)
         return lo + (hi - lo) * 0.5 * (u + 1.0)
 
-    state = venv.reset()
+    venv.reset()
+    last_rew = torch.zeros(a.envs, device=dev)
+
+    hold = {}
+
+    def seg_rollout_critic():
+        """Rollout step of all replicas + critic forward/backward; ends where the critic all-reduce goes."""
+        with torch.no_grad():                           # rollout of all replicas (rpo_ddpg.py:96-118, vectorised)
+            state = venv.state
+            act = proj.process_action(state, policy(actor, state, noise=0.1))
+            nxt, rew, done, _, _ = venv.step(act, inplace=True)
+            replay.extend(state=venv.prev_state, action=act, next_state=nxt, reward=rew, done=done.float())
+            last_rew.copy_(rew)
+        smp = replay.sample(a.batch)
+        hold["state"] = smp["state"]
+        with torch.no_grad():                           # critic target (rpo_ddpg.py:327-332)
+            na = proj.process_action(smp["next_state"], policy(actor_t, smp["next_state"]))
+            tq = smp["reward"] + 0.95 * (1 - smp["done"]) * critic_t(torch.cat([smp["next_state"], na], 1))
+        b_critic.zero_()
+        F.smooth_l1_loss(critic(torch.cat([smp["state"], smp["action"]], 1)), tq).backward()
+
+    def seg_critic_step(do_actor: bool):
+        """Critic optimiser step (+ actor forward/backward through the GRG kernel); ends at the actor all-reduce."""
+        opt_c.step()
+        if do_actor:                                    # actor loss (rpo_ddpg.py:307-324)
+            b_actor.zero_()
+            s = hold["state"]
+            act_c = env.complete_partial(s, policy(actor, s))          # autograd: GRG backward kernel
+            loss = (-critic(torch.cat([s, act_c], 1)) + nju(env.ineq_dist(s, act_c))).mean()
+            loss.backward()
+
+    def seg_actor_step():
+        opt_a.step()                                    # rpo_ddpg.py:199-205
+        opt_n.step()
+        with torch.no_grad():
+            nju.weight.clamp_(min=0)
+            for t, o in ((actor_t, actor), (critic_t, critic)):
+                for pt, po in zip(t.parameters(), o.parameters()):
+                    pt.lerp_(po, 0.005)
+
+    def iteration(do_actor: bool, run=None):
+        """Three segments separated by the two collectives, which always run eagerly (capturing NCCL collectives inside
+        the graph hung in our 2-GPU trial; an eager all-reduce of a 0.3-1.3 MB bucket costs one launch)."""
+        run = run or (lambda f, *args: f(*args))
+        run(seg_rollout_critic)
+        b_critic.all_reduce_mean()                      # the one collective of the critic step
+        run(seg_critic_step, do_actor)
+        if do_actor:
+            b_actor.all_reduce_mean()                   # the one collective of the actor step
+            run(seg_actor_step)
+
+    graphs = None
+    if a.graph:
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                   # warm-up outside capture (allocator, lazy init, optimiser state)
+            for w in range(3):
+                iteration(True)
+                iteration(False)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize()
+        graphs, pool = {}, torch.cuda.graph_pool_handle()
+        for key, fn, args in (("rc", seg_rollout_critic, ()), ("cs1", seg_critic_step, (True,)), ("cs0", seg_critic_step, (False,)),
+                              ("as", seg_actor_step, ())):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                fn(*args)
+            graphs[key] = g
+
+        def run_graph(fn, *args):
+            key = {seg_rollout_critic: "rc", seg_actor_step: "as"}.get(fn) or ("cs1" if args[0] else "cs0")
+            graphs[key].replay()
+    else:
+        for w in range(3):
+            iteration(True)
     n_proj = 0
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for it in range(a.iters):
-        with torch.no_grad():                           # rollout of all replicas (rpo_ddpg.py:96-118, vectorised)
-            act = proj.process_action(state, policy(actor, state, noise=0.1))
-            n_proj += a.envs
-            nxt, rew, done, _, _ = venv.step(act)
-            replay.extend(state=state, action=act, next_state=nxt, reward=rew, done=done.float())
-            state = nxt
-        smp = replay.sample(a.batch)
-        with torch.no_grad():                           # critic target (rpo_ddpg.py:327-332)
-            na = proj.process_action(smp["next_state"], policy(actor_t, smp["next_state"]))
-            n_proj += a.batch
-            tq = smp["reward"] + 0.95 * (1 - smp["done"]) * critic_t(torch.cat([smp["next_state"], na], 1))
-        b_critic.zero_()
-        F.smooth_l1_loss(critic(torch.cat([smp["state"], smp["action"]], 1)), tq).backward()
-        b_critic.all_reduce_mean()                      # the one collective of the critic step
-        opt_c.step()
-        if it % a.policy_fre == 0:                      # actor step (rpo_ddpg.py:184-205,307-324)
-            b_actor.zero_()
-            s = smp["state"]
-            act_c = env.complete_partial(s, policy(actor, s))          # autograd: GRG backward kernel
-            n_proj += a.batch
-            loss = (-critic(torch.cat([s, act_c], 1)) + nju(env.ineq_dist(s, act_c))).mean()
-            loss.backward()
-            b_actor.all_reduce_mean()
-            opt_a.step()
-            opt_n.step()
-            with torch.no_grad():
-                nju.weight.clamp_(min=0)
-                for t, o in ((actor_t, actor), (critic_t, critic)):
-                    for pt, po in zip(t.parameters(), o.parameters()):
-                        pt.lerp_(po, 0.005)
+        do_actor = it % a.policy_fre == 0
+        iteration(do_actor, run_graph if graphs is not None else None)
+        n_proj += a.envs + a.batch + (a.batch if do_actor else 0)
+    rew = last_rew
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     # replicas must still be identical (same broadcast start + same averaged gradients)
@@ -140,7 +189,7 @@ def main():
         n_all = float(n_proj)
     if rank == 0:
         print(json.dumps({"world": world, "iters": a.iters, "envs_per_gpu": a.envs, "batch_per_gpu": a.batch,
-                          "iters_per_s": a.iters / dt, "projected_actions_per_s": n_all / dt,
+                          "cuda_graph": bool(a.graph), "iters_per_s": a.iters / dt, "projected_actions_per_s": n_all / dt,
                           "env_steps_per_s": world * a.envs * a.iters / dt, "max_replica_drift": float(drift.item()),
                           "final_reward_mean": float(rew.mean()), "finite": bool(torch.isfinite(w).all())}))
     if world > 1:

@@ -33,15 +33,24 @@ def evopf_states(n: int, seed: int = 0, device="cpu") -> torch.Tensor:
     return torch.from_numpy(st).to(device)
 
 
+_BOX_CACHE = {}
+
+
 def evopf_partial_box(state: torch.Tensor):
     """(low, high) of the volatile partial-action box, float32, same device as ``state``
-    (EVOPFEnv.update evopf.py:769-783 with Battery.update_bound :127-143)."""
+    (EVOPFEnv.update evopf.py:769-783 with Battery.update_bound :127-143).  The constant rows are cached per device,
+    so the function performs no host->device copy after its first call (CUDA-graph capturable)."""
+    key = str(state.device)
+    if key not in _BOX_CACHE:
+        _BOX_CACHE[key] = (torch.tensor(K.ACTION_LOW[K.PARTIAL_ACTIONS], dtype=torch.float32, device=state.device),
+                           torch.tensor(K.ACTION_HIGH[K.PARTIAL_ACTIONS], dtype=torch.float32, device=state.device))
+    lo0, hi0 = _BOX_CACHE[key]
     n = state.shape[0]
-    low = torch.tensor(K.ACTION_LOW[K.PARTIAL_ACTIONS], dtype=torch.float32, device=state.device).repeat(n, 1)
-    high = torch.tensor(K.ACTION_HIGH[K.PARTIAL_ACTIONS], dtype=torch.float32, device=state.device).repeat(n, 1)
     soc = state[:, 28:33].double()
-    high[:, -5:] = ((1.0 / K.ETA_IN) * torch.clamp(K.B_HIGH - soc, max=K.B_PMAX)).float()
-    low[:, -5:] = (K.ETA_OUT * torch.clamp(K.B_LOW - soc, min=K.B_PMIN)).float()
+    hi_e = ((1.0 / K.ETA_IN) * torch.clamp(K.B_HIGH - soc, max=K.B_PMAX)).float()
+    lo_e = (K.ETA_OUT * torch.clamp(K.B_LOW - soc, min=K.B_PMIN)).float()
+    low = torch.cat([lo0[:-5].expand(n, 9), lo_e], dim=1)
+    high = torch.cat([hi0[:-5].expand(n, 9), hi_e], dim=1)
     return low, high
 
 

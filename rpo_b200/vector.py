@@ -22,10 +22,13 @@ class EvopfExoSampler(object):
     (data/demand.py:47-67, data/price.py:40-47): case share mixed with Dirichlet(1) over the 11 load buses (rho = .5),
     total load following a daily curve, qd = pd tan(acos(U(.9,1))) sign(Qd), price = curve (1+N)(1+.1 N)/100."""
 
-    def __init__(self, device, seed: int = 0, T: int = 24):
+    def __init__(self, device, seed: int = 0, T: int = 24, default_generator: bool = False):
+        """default_generator=True draws from torch's default generator of the device (which CUDA-graph capture
+        supports) instead of a private seeded one."""
         self.device = torch.device(device)
         self.T = T
-        self.gen = torch.Generator(device=self.device).manual_seed(seed)
+        self.gen = None if default_generator else torch.Generator(device=self.device).manual_seed(seed)
+        self.ar24 = torch.arange(24, device=self.device)
         bus = case14()["bus"]
         pd_case = torch.tensor(bus[:, PD], dtype=torch.float64)
         self.share = (pd_case / pd_case.sum()).to(self.device, torch.float32)
@@ -51,8 +54,8 @@ class EvopfExoSampler(object):
         pd = ratio * (self.total * self.demand_curve[hour])[:, None]
         pf = 0.9 + 0.1 * self._rand(n, 14)
         qd = pd * torch.tan(torch.acos(pf)) * self.q_sign[None]
-        idx = (hour[:, None] + torch.arange(24, device=self.device)[None]) % self.T
-        ahead_valid = (hour[:, None] + torch.arange(24, device=self.device)[None]) < self.T
+        idx = (hour[:, None] + self.ar24[None]) % self.T
+        ahead_valid = (hour[:, None] + self.ar24[None]) < self.T
         price = self.price_curve[idx] * (1 + self._randn(n, 24)) * (1 + 0.1 * self._randn(n, 1)) * ahead_valid
         return torch.cat([pd, qd, price], dim=1).float()
 
@@ -61,9 +64,9 @@ class EvopfVectorEnv(object):
     """N independent EVOPF-v0 replicas on one GPU; `step` = one launch of rpo_evopf_step (evopf.py:348-366 row-wise).
     Episodes last T = 24 steps (demand.py:69-75) and restart automatically (soc back to 0.2, evopf.py:62-63,243)."""
 
-    def __init__(self, n: int, device, seed: int = 0):
+    def __init__(self, n: int, device, seed: int = 0, default_generator: bool = False):
         self.n, self.device = n, torch.device(device)
-        self.exo = EvopfExoSampler(self.device, seed)
+        self.exo = EvopfExoSampler(self.device, seed, default_generator=default_generator)
         self.T = self.exo.T
         self.hour = torch.zeros(n, dtype=torch.int64, device=self.device)
         self.state = None
@@ -75,44 +78,54 @@ class EvopfVectorEnv(object):
         self.state = torch.cat([rows[:, :28], soc, rows[:, 28:]], dim=1).contiguous()
         return self.state
 
-    def step(self, action: torch.Tensor):
-        """action (N,43) -> next_state (N,57), reward (N,), done (N,) bool, eq_viol (N,28), ineq_viol (N,58)."""
+    def step(self, action: torch.Tensor, inplace: bool = False):
+        """action (N,43) -> next_state (N,57), reward (N,), done (N,) bool, eq_viol (N,28), ineq_viol (N,58).
+        inplace=True keeps `self.state` in ONE buffer (needed under CUDA-graph capture): the pre-step state is saved in
+        `self.prev_state` and the buffer is overwritten with the next state."""
         nxt_hour = self.hour + 1
         done = nxt_hour >= self.T
         rows = self.exo.rows(torch.where(done, torch.zeros_like(nxt_hour), nxt_hour))
         ns, rew, eqv, iqv = ops.evopf_step(self.state, action, rows)
-        if bool(done.any()):
-            ns = ns.clone()
-            ns[done, 28:33] = K.B_LOW + 0.1
-        self.hour = torch.where(done, torch.zeros_like(nxt_hour), nxt_hour)
-        self.state = ns
+        # episode restart without a host round trip: soc back to its initial value where the day is over
+        soc = torch.where(done[:, None], torch.full_like(ns[:, 28:33], K.B_LOW + 0.1), ns[:, 28:33])
+        ns = torch.cat([ns[:, :28], soc, ns[:, 33:]], dim=1)
+        self.hour.copy_(torch.where(done, torch.zeros_like(nxt_hour), nxt_hour))
+        if inplace:
+            self.prev_state = self.state.clone()
+            self.state.copy_(ns)
+        else:
+            self.prev_state = self.state
+            self.state = ns
         return ns, rew, done, eqv, iqv
 
 
 class DeviceReplay(object):
-    """Ring buffer of transitions in HBM with uniform sampling on the device (reference: utils/buffer.py:3-34)."""
+    """Ring buffer of transitions in HBM with uniform sampling on the device (reference: utils/buffer.py:3-34).
+    Write pointer and fill level live on the device too, so extend() / sample() issue no host synchronisation and can
+    be captured in a CUDA graph (`default_generator=True` then draws from torch's graph-safe default generator)."""
 
-    def __init__(self, capacity: int, device, **shapes: int):
+    def __init__(self, capacity: int, device, default_generator: bool = False, **shapes: int):
         self.capacity, self.device = int(capacity), torch.device(device)
         self.buf: Dict[str, torch.Tensor] = {k: torch.zeros(self.capacity, d, device=self.device) for k, d in shapes.items()}
-        self.pointer = 0
-        self.size = 0
-        self.gen = torch.Generator(device=self.device).manual_seed(1234)
+        self.ptr = torch.zeros((), dtype=torch.int64, device=self.device)
+        self.fill = torch.zeros((), dtype=torch.int64, device=self.device)
+        self.gen = None if default_generator else torch.Generator(device=self.device).manual_seed(1234)
 
     def __len__(self):
-        return self.size
+        return int(self.fill.item())
 
     def extend(self, **rows: torch.Tensor):
         n = next(iter(rows.values())).shape[0]
-        idx = (self.pointer + torch.arange(n, device=self.device)) % self.capacity
+        idx = (self.ptr + torch.arange(n, device=self.device)) % self.capacity
         for k, v in rows.items():
-            self.buf[k][idx] = v.view(n, -1).to(self.buf[k].dtype)
-        self.pointer = (self.pointer + n) % self.capacity
-        self.size = min(self.size + n, self.capacity)
+            self.buf[k].index_copy_(0, idx, v.reshape(n, -1).to(self.buf[k].dtype))
+        self.ptr.copy_((self.ptr + n) % self.capacity)
+        self.fill.copy_(torch.clamp(self.fill + n, max=self.capacity))
 
     def sample(self, num: int) -> Dict[str, torch.Tensor]:
-        idx = torch.randint(0, self.size, (num,), generator=self.gen, device=self.device)
-        return {k: v[idx] for k, v in self.buf.items()}
+        u = torch.rand(num, generator=self.gen, device=self.device)
+        idx = torch.clamp((u * self.fill).long(), max=self.capacity - 1)
+        return {k: v.index_select(0, idx) for k, v in self.buf.items()}
 
 
 @torch.no_grad()
