@@ -158,6 +158,18 @@ class EVOPFEnv(object):
     def ineq_partial_grad(self, state, action, eps=0.0):        # evopf.py:596-612 (eps is ignored there too)
         return ops.evopf_direction(state, action)
 
+    def ineq_grad_new(self, state, action, eps=0.0):            # evopf.py:590-594: ineq_jac^T . 1[ineq_dist > 0]
+        """The constant +-1 selector `ineq_jac` (evopf.py:663-707) is never built: the product is the sign-of-violation
+        vector, assembled on the device from the residual kernel's output."""
+        m = (self.ineq_resid(state, action) > 0).to(torch.float32)
+        ng, nb = self.ng, self.nbus
+        d = torch.zeros(action.shape[0], self.ydim, dtype=torch.float32, device=action.device)
+        d[:, 0:ng] = m[:, 0:ng] - m[:, ng:2 * ng]
+        d[:, ng:2 * ng] = m[:, 2 * ng:3 * ng] - m[:, 3 * ng:4 * ng]
+        d[:, 2 * ng:2 * ng + nb] = m[:, 4 * ng:4 * ng + nb] - m[:, 4 * ng + nb:4 * ng + 2 * nb]
+        d[:, -self.ne:] = m[:, 4 * ng + 2 * nb:5 * ng + 2 * nb] - m[:, 5 * ng + 2 * nb:]
+        return d
+
     def ineq_dist_np(self, state, action):                      # evopf.py:569-572
         return self.ineq_dist(self._t(state), self._t(action)).cpu().numpy()
 

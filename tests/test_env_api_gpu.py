@@ -55,6 +55,7 @@ def test_evopf_env_protocol_and_autograd(evopf_oracle):
     yd = y.detach()
     assert (env.eq_resid(s_d.detach(), yd).cpu() - orc.eq_resid(st, yd.cpu())).abs().max() < 2e-5
     assert (env.ineq_dist(s_d.detach(), yd).cpu() - orc.ineq_dist(st, yd.cpu())).abs().max() < 1e-6
+    assert torch.equal(env.ineq_grad_new(s_d.detach(), yd).cpu(), orc.ineq_grad_new(st, yd.cpu()))
     lo, hi = env.update(st)
     lo_o, hi_o = orc.partial_box(st)
     assert np.array_equal(lo, lo_o) and np.array_equal(hi, hi_o)
