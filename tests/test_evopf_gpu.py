@@ -163,3 +163,22 @@ def test_unaligned_views_take_the_fallback_path():
     torch.cuda.synchronize()
     yc_ref, _, _, _ = ops.evopf_project(st_d, z_d, 1e-4, 0.0, 1e-5, 10)
     assert torch.equal(big_yc[1:].view(B, 43), yc_ref)
+
+
+def test_step_and_resid_optional_outputs():
+    """Nullable outputs of the C ABI (eq / ineq / violations) on the TMA path (full CTAs) and the ragged path."""
+    from rpo_b200 import ops, synth
+    for B in (128 * 5, 128 * 5 + 37):
+        st, z = _inputs(B, "D1", seed=55)
+        st_d = st.cuda()
+        y = ops.evopf_complete_fwd(st_d, z.cuda())
+        eq, iq = ops.evopf_resid(st_d, y)
+        eq1, none1 = ops.evopf_resid(st_d, y, want_ineq=False)
+        none2, iq2 = ops.evopf_resid(st_d, y, want_eq=False)
+        assert none1 is None and none2 is None and torch.equal(eq, eq1) and torch.equal(iq, iq2)
+        nxt = synth.evopf_states(B, seed=56)
+        exo = torch.cat([nxt[:, :28], nxt[:, 33:]], dim=1).contiguous().cuda()
+        ns, rew, eqv, iqv = ops.evopf_step(st_d, y, exo)
+        ns2, rew2, e2, i2 = ops.evopf_step(st_d, y, exo, want_viol=False)
+        assert e2 is None and i2 is None and torch.equal(ns, ns2) and torch.equal(rew, rew2)
+        assert torch.equal(eqv, eq) and torch.equal(iqv, torch.clamp(iq, 0))
