@@ -28,6 +28,7 @@ import torch.nn as nn  # noqa: E402
 import torch.nn.functional as F  # noqa: E402
 
 from rpo_b200.algo import RPOProjectionMixin  # noqa: E402
+from rpo_b200.box import BoxConstraint  # noqa: E402
 from rpo_b200.dist import FlatGradBucket, broadcast_parameters  # noqa: E402
 from rpo_b200.env import EVOPFEnv  # noqa: E402
 from rpo_b200.vector import DeviceReplay, EvopfVectorEnv  # noqa: E402
@@ -68,8 +69,9 @@ def main():
     env = EVOPFEnv(device=dev)
     proj = Projector(env, a)
     venv = EvopfVectorEnv(a.envs, dev, seed=rank, default_generator=a.graph)
-    actor, critic = mlp(57, 14, out_act=nn.Tanh()).to(dev), mlp(57 + 43, 1).to(dev)
-    actor_t, critic_t = mlp(57, 14, out_act=nn.Tanh()).to(dev), mlp(57 + 43, 1).to(dev)
+    box = BoxConstraint(*env.box_constraint_partial, device=dev, volatile=env.volatile, update=env.update)
+    actor, critic = mlp(57, 14).to(dev), mlp(57 + 43, 1).to(dev)
+    actor_t, critic_t = mlp(57, 14).to(dev), mlp(57 + 43, 1).to(dev)
     nju = nn.Linear(58, 1, bias=False).to(dev)
     nn.init.zeros_(nju.weight)
     broadcast_parameters([actor, critic, nju])
@@ -83,11 +85,11 @@ def main():
     replay = DeviceReplay(a.envs * 64, dev, default_generator=a.graph, state=57, action=43, next_state=57, reward=1, done=1)
 
     def policy(net, s, noise=0.0):
-        lo, hi = env.update_device(s)                   # volatile box on the device (f-1)
-        u = net(s)
-        if noise:
-            u = (u + noise * torch.randn_like(u)).clamp(-1, 1)
-        return lo + (hi - lo) * 0.5 * (u + 1.0)
+        """box(tanh(net(s)), s) with the state-dependent battery bounds: ONE launch of rpo_box_fwd (f-1; policy.py:30-31)."""
+        if not noise:
+            return box.squash(net(s), s)
+        u = torch.tanh(net(s))
+        return box((u + noise * torch.randn_like(u)).clamp(-1, 1), s)
 
     venv.reset()
     last_rew = torch.zeros(a.envs, device=dev)

@@ -130,6 +130,23 @@ int rpo_pen_resid(const float* obs, const float* a, float* eq, float* ineq, int6
 int rpo_pen_step(const float* st, const float* a, float* next_st, float* next_obs, float* reward, int32_t* done,
                  float* eq_viol, float* ineq_viol, int64_t B, void* stream);
 
+/* ------------------------------------------------------------------ action box ------------- */
+/* BoxConstraint: squash / clip of a policy output into the (state-dependent) action box, one launch, no host round
+ * trip.  Replaces rpo/algo/model/utils.py:40-51 (__call__), :92-104 (clip), :106-118 (action_scale), :75-90 (update_box)
+ * and, for EVOPF, EVOPFEnv.update rpo/env/electrical_grid/evopf.py:769-783 + Battery.update_bound :127-143, which the
+ * reference evaluates through numpy on the host on every actor forward (D2H + 4 x H2D).
+ * x, out (B, width); lo / hi (width) device arrays with the constant bounds; the LAST n_vol columns (0, or 5 = the EVOPF
+ * batteries) take their bounds from soc (B rows, leading dimension ld_soc floats; pass state + 28, ld 57):
+ * hi = min(0.2, 0.8 - soc) / 0.9, lo = 0.9 max(-0.2, 0.1 - soc) in float64, rounded to float32.
+ * mode: 0 scale*x+base (style "tanh") | 1 scale*tanh(x)+base (policy.py:30-31 fused) | 2 clip | 3 (hi-lo)*x+lo (style
+ * "sigmoid") | 4 scale | 5 lo | 6 hi (x may be NULL for 4-6).  out may alias x. */
+int rpo_box_fwd(const float* x, const float* lo, const float* hi, int width, const float* soc, int ld_soc, int n_vol,
+                float* out, int mode, int64_t B, void* stream);
+/* grad_x = grad_out . d out / d x for modes 0-3 (clip: torch.clip's mask lo <= x <= hi).  No gradient reaches the state,
+ * as in the reference (its bounds leave the autograd graph through numpy). */
+int rpo_box_bwd(const float* x, const float* grad_out, const float* lo, const float* hi, int width, const float* soc,
+                int ld_soc, int n_vol, float* grad_x, int mode, int64_t B, void* stream);
+
 /* ------------------------------------------------------------------ host-buffer helpers ----------------------- */
 /* Copy the first `ncols` floats of each of `nrows` rows between a HOST matrix (pinned for asynchrony; leading dimension
  * ld_host floats) and a DEVICE matrix (leading dimension ld_dev floats): one strided DMA (cudaMemcpy2DAsync) on `stream`.

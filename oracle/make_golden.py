@@ -164,11 +164,58 @@ def pen():
              step_reward=np.array(rews), step_done=np.array(dones), step_ineq_viol=np.stack(iv), step_eq_viol=np.stack(ev))
 
 
+def box():
+    """BoxConstraint (rpo/algo/model/utils.py:5-118) on the EVOPF volatile partial box and on static boxes."""
+    rpo = load_reference()
+    from rpo.algo.model.utils import BoxConstraint
+    import contextlib
+    import io
+    env = make_cpu_env("evopf")
+    cpu = torch.device("cpu")
+    with contextlib.redirect_stdout(io.StringIO()):           # the constructor prints its arrays
+        bx = BoxConstraint(*env.box_constraint_partial, device=cpu, volatile=env.volatile, update=env.update)
+        bx_sig = BoxConstraint(*env.box_constraint_partial, device=cpu, style="sigmoid", volatile=True, update=env.update)
+        bx_full = BoxConstraint(*env.box_constraint, device=cpu)
+    Bn = 64
+    st = synth.evopf_states(Bn, seed=300)
+    st[:4, 28:33] = torch.tensor([[0.1, 0.8, 0.6, 0.3, 0.75], [0.05, 0.9, 0.45, 0.1, 0.8], [0.6000001, 0.3, 0.2999999, 0.5, 0.7],
+                                  [0.2, 0.2, 0.2, 0.2, 0.2]])
+    g = torch.Generator().manual_seed(301)
+    pre = (1.5 * torch.randn(Bn, 14, generator=g)).float()
+    up = torch.randn(Bn, 14, generator=g).float()
+    out = {"state": st.numpy(), "pre": pre.numpy(), "up": up.numpy()}
+    x = pre.clone().requires_grad_(True)
+    z = bx(torch.tanh(x), st)
+    z.backward(up)
+    out["tanh_call"], out["tanh_call_grad"] = z.detach().numpy(), x.grad.numpy()
+    t = torch.tanh(pre).requires_grad_(True)
+    z = bx(t, st)
+    z.backward(up)
+    out["call"], out["call_grad"], out["call_in"] = z.detach().numpy(), t.grad.numpy(), t.detach().numpy()
+    lo, hi = env.update(st)
+    out["low"], out["high"] = lo, hi
+    raw = (torch.tensor(lo) + (torch.tensor(hi) - torch.tensor(lo)) * (torch.rand(Bn, 14, generator=g) * 1.6 - 0.3)).float()
+    raw[0, :3] = torch.tensor(lo[0, :3])                      # exactly on the bounds: torch.clip passes the gradient
+    raw[0, 9:12] = torch.tensor(hi[0, 9:12])
+    r = raw.clone().requires_grad_(True)
+    c = bx.clip(r, st)
+    c.backward(up)
+    out["raw"], out["clip"], out["clip_grad"] = raw.numpy(), c.detach().numpy(), r.grad.numpy()
+    out["scale"] = bx.action_scale(st).numpy()
+    u01 = torch.rand(Bn, 14, generator=g).float()
+    out["u01"], out["sigmoid_call"] = u01.numpy(), bx_sig(u01, st).numpy()
+    x43 = (torch.rand(Bn, 43, generator=g) * 2 - 1).float()
+    out["x43"], out["full_call"] = x43.numpy(), bx_full(x43).numpy()
+    out["full_clip"] = bx_full.clip(3 * x43).numpy()
+    out["full_low"], out["full_high"] = env.box_constraint
+    np.savez(os.path.join(OUT, "box.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
-    evopf()
-    cart()
-    pen()
+    which = sys.argv[1:] or ["evopf", "cart", "pen", "box"]
+    for name in which:
+        {"evopf": evopf, "cart": cart, "pen": pen, "box": box}[name]()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

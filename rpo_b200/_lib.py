@@ -44,6 +44,8 @@ SIGNATURES = {
     "rpo_pen_project": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_int, _P, _P]),
     "rpo_pen_resid": (c_int, [_P, _P, _P, _P, c_int64, _P]),
     "rpo_pen_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
+    "rpo_box_fwd": (c_int, [_P, _P, _P, c_int, _P, c_int, c_int, _P, c_int, c_int64, _P]),
+    "rpo_box_bwd": (c_int, [_P, _P, _P, _P, c_int, _P, c_int, c_int, _P, c_int, c_int64, _P]),
     "rpo_copy_rows_h2d": (c_int, [_P, c_int, _P, c_int, c_int, c_int64, _P]),
     "rpo_copy_rows_d2h": (c_int, [_P, c_int, _P, c_int, c_int, c_int64, _P]),
     "rpo_fp32_peak_probe": (c_int, [_P, c_int, c_int, c_int, _P]),

@@ -83,6 +83,7 @@ class EVOPFEnv(object):
         self.p_data = PriceLoader(T=24, ahead=self.nahead, regularized=True, reg_bias=0.1, reg_sigma=0.05,
                                   curve=price_curve, pickle_path=pp)                      # evopf.py:216
         self.nbus, self.ng, self.ne = K.NBUS, K.NG, K.NE
+        self._box_dev = {}
         self.genbase, self.baseMVA = K.GENBASE.copy(), K.BASE_MVA
         self.slack, self.pv, self.spv, self.pq = K.SLACK.copy(), K.PV.copy(), K.SPV.copy(), K.PQ.copy()
         self.slack_, self.pv_, self.spv_ = K.SLACK_.copy(), K.PV_.copy(), K.SPV_.copy()
@@ -211,10 +212,17 @@ class EVOPFEnv(object):
         high[:, -self.ne:] = new_p_max
         return low, high
 
-    def update_device(self, state: torch.Tensor):
-        """Same box as update(), computed on the device without a host round trip (float64 then rounded, as numpy does)."""
-        from ..synth import evopf_partial_box
-        return evopf_partial_box(state)
+    def update_device(self, state: torch.Tensor, full: bool = False):
+        """Same box as update(), computed on the device without a host round trip: two launches of rpo_box_fwd
+        (bounds in float64 then rounded, as numpy does).  Policies should not need it: `rpo_b200.box.BoxConstraint`
+        squashes / clips against the volatile box in one launch."""
+        key = (str(state.device), bool(full))
+        if key not in self._box_dev:
+            lo, hi = self.box_constraint if full else self.box_constraint_partial
+            self._box_dev[key] = (torch.tensor(lo, dtype=torch.float32, device=state.device),
+                                  torch.tensor(hi, dtype=torch.float32, device=state.device))
+        lo, hi = self._box_dev[key]
+        return (ops.box_fwd(None, lo, hi, ops.BOX_LOW, state, self.ne), ops.box_fwd(None, lo, hi, ops.BOX_HIGH, state, self.ne))
 
     # ---- gym API (evopf.py:348-380) -----------------------------------------------------------------------
     def reset(self):

@@ -321,6 +321,57 @@ def pen_step(st, a, want_viol=True):
     return nst, nobs, rew, done, eqv, iqv
 
 
+# ------------------------------------------------------------------------------------------- action box (f-1)
+BOX_AFFINE, BOX_TANH, BOX_CLIP, BOX_AFFINE01, BOX_SCALE, BOX_LOW, BOX_HIGH = range(7)
+
+
+def _box_args(x, lo, hi, state, n_vol, mode, B):
+    lo = _dev(lo, "lo").view(-1)
+    hi = _dev(hi, "hi").view(-1)
+    W = lo.numel()
+    if hi.numel() != W:
+        raise ValueError("lo and hi disagree on the box width")
+    if mode <= BOX_AFFINE01:
+        x = _dev(x, "x", W)
+        B = x.shape[0]
+    elif B is None:
+        if state is None:
+            raise ValueError("modes scale / low / high need `state` or `B` for the batch size")
+        B = state.shape[0] if state.dim() > 1 else 1
+    soc_ptr, ld = None, 0
+    if n_vol:
+        if state is None:
+            raise ValueError("a volatile box needs the state (EVOPFEnv.update)")
+        state, ld = _rows(state, "state", 33)
+        if state.shape[0] != B:
+            raise ValueError("state and x disagree on the batch size")
+        soc_ptr = state.data_ptr() + 28 * 4
+    return x, lo, hi, W, state, soc_ptr, ld, B
+
+
+def box_fwd(x, lo, hi, mode: int = BOX_AFFINE, state=None, n_vol: int = 0, out=None, B=None):
+    """One launch of rpo_box_fwd: x (B,W) -> (B,W) inside the box [lo, hi] whose last n_vol columns follow state[:, 28:33]."""
+    lib = _lib.load()
+    x, lo, hi, W, state, soc_ptr, ld, B = _box_args(x, lo, hi, state, n_vol, mode, B)
+    if out is None:
+        out = torch.empty(B, W, dtype=torch.float32, device=lo.device)
+    with torch.cuda.device(lo.device):
+        _lib.check(lib.rpo_box_fwd(_ptr(x) if mode <= BOX_AFFINE01 else None, lo.data_ptr(), hi.data_ptr(), W, soc_ptr, ld, n_vol,
+                                   out.data_ptr(), mode, B, _stream(lo)), "rpo_box_fwd")
+    return out
+
+
+def box_bwd(x, grad_out, lo, hi, mode: int = BOX_AFFINE, state=None, n_vol: int = 0):
+    lib = _lib.load()
+    x, lo, hi, W, state, soc_ptr, ld, B = _box_args(x, lo, hi, state, n_vol, mode, None)
+    g = _dev(grad_out, "grad_out", W)
+    gx = torch.empty(B, W, dtype=torch.float32, device=lo.device)
+    with torch.cuda.device(lo.device):
+        _lib.check(lib.rpo_box_bwd(x.data_ptr(), g.data_ptr(), lo.data_ptr(), hi.data_ptr(), W, soc_ptr, ld, n_vol, gx.data_ptr(),
+                                   mode, B, _stream(lo)), "rpo_box_bwd")
+    return gx
+
+
 def fp32_peak_probe(device, blocks: int, threads: int, iters: int):
     """Launch the FMA micro-kernel once; returns flops executed (time it with CUDA events around the call)."""
     lib = _lib.load()

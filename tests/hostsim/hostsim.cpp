@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include "../../rpo_b200/csrc/evopf_core.cuh"
 #include "../../rpo_b200/csrc/classic_core.cuh"
+#include "../../rpo_b200/csrc/box_core.cuh"
 
 extern "C" {
 
@@ -160,6 +161,27 @@ void hs_pen_resid(const real* obs, const real* a, real* eq, real* ineq, int B) {
 void hs_pen_step(const real* st, const real* a, real* nst, real* nobs, real* reward, int* done, int B) {
     for (int b = 0; b < B; ++b)
         done[b] = pen_step(st + 4 * (long)b, a + 2 * (long)b, nst + 4 * (long)b, nobs + 5 * (long)b, reward + b);
+}
+
+// action box (box_core.cuh), same element order as k_box
+static void hs_box(int bwd, const real* x, const real* g, const real* lo_c, const real* hi_c, int W, const real* soc, int ld_soc,
+                   int n_vol, real* out, int mode, int B) {
+    for (int b = 0; b < B; ++b)
+        for (int c = 0; c < W; ++c) {
+            real lo, hi;
+            if (c >= W - n_vol) evopf_pe_bound1(soc[(long)b * ld_soc + (c - (W - n_vol))], &hi, &lo);
+            else { lo = lo_c[c]; hi = hi_c[c]; }
+            const long e = (long)b * W + c;
+            const real xv = x ? x[e] : RC(0.0);
+            out[e] = bwd ? box_bwd(xv, lo, hi, g[e], mode) : box_fwd(xv, lo, hi, mode);
+        }
+}
+void hs_box_fwd(const real* x, const real* lo, const real* hi, int W, const real* soc, int ld_soc, int n_vol, real* out, int mode, int B) {
+    hs_box(0, x, (const real*)0, lo, hi, W, soc, ld_soc, n_vol, out, mode, B);
+}
+void hs_box_bwd(const real* x, const real* g, const real* lo, const real* hi, int W, const real* soc, int ld_soc, int n_vol, real* gx,
+                int mode, int B) {
+    hs_box(1, x, g, lo, hi, W, soc, ld_soc, n_vol, gx, mode, B);
 }
 
 int hs_sizeof_real() { return (int)sizeof(real); }

@@ -208,7 +208,38 @@ def pen_step(st, a, want_viol=True):
     return _t(nst), _t(nobs), _t(rew), _t(done), (eq if want_viol else None), (torch.clamp(iq, 0) if want_viol else None)
 
 
-NAMES = [n for n in dir() if n.startswith(("evopf_", "cart_", "pen_"))]
+def _box(bwd, x, g, lo, hi, mode, state, n_vol, B):
+    lo_, hi_ = _np(lo).reshape(-1), _np(hi).reshape(-1)
+    W = lo_.size
+    xx = None if x is None else _np(x, W)
+    if xx is not None:
+        B = xx.shape[0]
+    elif B is None:
+        B = _np(state).shape[0]
+    soc, ld = None, 0
+    if n_vol:
+        s = _np(state)
+        if s.shape[0] != B:
+            s = np.ascontiguousarray(np.broadcast_to(s, (B, s.shape[1])))
+        soc, ld = np.ascontiguousarray(s[:, 28:33]), 5
+    out = np.zeros((B, W), np.float32)
+    if bwd:
+        gg = _np(g, W)
+        lib().hs_box_bwd(_P(xx), _P(gg), _P(lo_), _P(hi_), W, _P(soc), ld, n_vol, _P(out), mode, B)
+    else:
+        lib().hs_box_fwd(_P(xx), _P(lo_), _P(hi_), W, _P(soc), ld, n_vol, _P(out), mode, B)
+    return _t(out)
+
+
+def box_fwd(x, lo, hi, mode=0, state=None, n_vol=0, out=None, B=None):
+    return _box(False, x, None, lo, hi, mode, state, n_vol, B)
+
+
+def box_bwd(x, grad_out, lo, hi, mode=0, state=None, n_vol=0):
+    return _box(True, x, grad_out, lo, hi, mode, state, n_vol, None)
+
+
+NAMES = [n for n in dir() if n.startswith(("evopf_", "cart_", "pen_", "box_"))]
 
 
 def install(monkeypatch):

@@ -406,13 +406,15 @@ class Gen(object):
         e("}")
         e("")
         e("// Battery bounds in float64 then rounded, as Battery.ineq_resid does in numpy (evopf.py:109-116).")
+        e("// One battery (the same numbers are the volatile action-box rows: Battery.update_bound evopf.py:127-143).")
+        e("RPO_HD void evopf_pe_bound1(real soc, real* pe_max, real* pe_min) {")
+        e("    const double s = (double)soc;")
+        e("    const double hi = (1.0 / %r) * fmin(%r, %r - s);" % (K.ETA_IN, K.B_PMAX, K.B_HIGH))
+        e("    const double lo = %r * fmax(%r, %r - s);" % (K.ETA_OUT, K.B_PMIN, K.B_LOW))
+        e("    *pe_max = (real)hi; *pe_min = (real)lo;")
+        e("}")
         e("RPO_HD void evopf_pe_bounds(const real* soc, real* pe_max, real* pe_min) {")
-        e("    for (int g = 0; g < 5; ++g) {")
-        e("        const double s = (double)soc[g];")
-        e("        const double hi = (1.0 / %r) * fmin(%r, %r - s);" % (K.ETA_IN, K.B_PMAX, K.B_HIGH))
-        e("        const double lo = %r * fmax(%r, %r - s);" % (K.ETA_OUT, K.B_PMIN, K.B_LOW))
-        e("        pe_max[g] = (real)hi; pe_min[g] = (real)lo;")
-        e("    }")
+        e("    for (int g = 0; g < 5; ++g) evopf_pe_bound1(soc[g], pe_max + g, pe_min + g);")
         e("}")
         e("")
         e("// ineq_resid (evopf.py:548-563): 58 rows; returns max ineq_dist; optionally stores the residuals;")

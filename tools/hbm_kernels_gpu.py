@@ -42,6 +42,17 @@ exo = torch.cat([s[:, :28], s[:, 33:]], 1).contiguous()
 rep('evopf_resid', timeit(lambda: ops.evopf_resid(s, y)), 132 + 172 + 112 + 232, B2)
 rep('evopf_step (+viol)', timeit(lambda: ops.evopf_step(s, y, exo)), 228 + 172 + 208 + 228 + 4 + 112 + 232, B2)
 rep('evopf_step (no viol)', timeit(lambda: ops.evopf_step(s, y, exo, want_viol=False)), 228 + 172 + 208 + 228 + 4, B2)
+from rpo_b200.box import BoxConstraint
+from rpo_b200 import evopf_constants as K
+bx = BoxConstraint(K.ACTION_LOW[K.PARTIAL_ACTIONS], K.ACTION_HIGH[K.PARTIAL_ACTIONS], device='cuda', volatile=True)
+pre = torch.randn(B2, 14, device='cuda'); up = torch.randn(B2, 14, device='cuda')
+rep('box squash (tanh, volatile)', timeit(lambda: ops.box_fwd(pre, bx.cmin_torch, bx.cmax_torch, ops.BOX_TANH, s, 5)), 56 + 56 + 20, B2)
+rep('box clip (volatile)', timeit(lambda: ops.box_fwd(pre, bx.cmin_torch, bx.cmax_torch, ops.BOX_CLIP, s, 5)), 56 + 56 + 20, B2)
+rep('box squash bwd', timeit(lambda: ops.box_bwd(pre, up, bx.cmin_torch, bx.cmax_torch, ops.BOX_TANH, s, 5)), 56 * 3 + 20, B2)
+def torch_box():
+    lo, hi = synth.evopf_partial_box(s); sc = (hi - lo) / 2
+    return sc * torch.tanh(pre) + (lo + sc)
+rep('  same in torch ops (device)', timeit(torch_box), 56 + 56 + 20, B2)
 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
 src = torch.empty(1 << 28, dtype=torch.float32, device='cuda'); dst = torch.empty_like(src)
 for _ in range(3): dst.copy_(src)
