@@ -71,9 +71,11 @@ class RPOProjectionMixin(object):
         return yc if train else (yc, k)
 
 
-def install(rpo_module=None, register_envs: bool = True):
+def install(rpo_module=None, register_envs: bool = True, box: bool = True):
     """Route the reference's own RPODDPG / RPOSAC through the B200 path: patches
-    process_action / grad_steps on the two classes and re-registers the gym ids to rpo_b200.env classes."""
+    process_action / grad_steps on the two classes, re-registers the gym ids to rpo_b200.env classes and (box=True)
+    makes both agents construct rpo_b200.box.BoxConstraint (one launch per squash / clip) instead of
+    rpo/algo/model/utils.py's host round trip (rpo_ddpg.py:28,63; rpo_sac.py:29,67)."""
     if rpo_module is None:
         import rpo as rpo_module           # the reference package
     import rpo.algo as ralgo
@@ -81,6 +83,11 @@ def install(rpo_module=None, register_envs: bool = True):
         cls.process_action = RPOProjectionMixin.process_action
         cls.grad_steps = RPOProjectionMixin.grad_steps
         cls.exact_loop_exit = True
+    if box:
+        import importlib
+        from .box import BoxConstraint
+        for name in ("rpo.algo.rpo_ddpg", "rpo.algo.rpo_sac"):
+            importlib.import_module(name).BoxConstraint = BoxConstraint
     if register_envs:
         from .env import register_all
         register_all(force=True)

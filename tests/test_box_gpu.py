@@ -81,7 +81,8 @@ def test_full_size_inside_box(box):
     st = synth.evopf_states(B, seed=9, device="cuda")
     lo, hi = synth.evopf_partial_box(st)
     z = box.squash(torch.randn(B, 14, device="cuda") * 3, st)
-    assert bool((z >= lo).all()) and bool((z <= hi).all())
+    # scale * (+-1) + (lo + scale) may land one rounding step outside the box, in the reference as well
+    assert bool((z >= lo - 2e-7).all()) and bool((z <= hi + 2e-7).all())
     c = box.clip(z + 0.05 * torch.randn_like(z), st)
     assert bool((c >= lo).all()) and bool((c <= hi).all())
     assert torch.equal(box.clip(c, st), c)                      # idempotent

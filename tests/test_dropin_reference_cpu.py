@@ -28,9 +28,16 @@ def dropin(monkeypatch):
     import rpo_b200.algo as balgo
     saved = {cls: (cls.process_action, cls.grad_steps) for cls in (ralgo.RPODDPG, ralgo.RPOSAC)}
     saved_registry = dict(gym.envs.registration.registry)
+    import importlib
+    mods = [importlib.import_module(n) for n in ("rpo.algo.rpo_ddpg", "rpo.algo.rpo_sac")]
+    saved_box = [m.BoxConstraint for m in mods]
     hostsim_ops.install(monkeypatch)
     balgo.install(rpo)
+    from rpo_b200.box import BoxConstraint as B200Box
+    assert all(m.BoxConstraint is B200Box for m in mods)          # the agents now build the one-launch box
     yield rpo
+    for m, b in zip(mods, saved_box):
+        m.BoxConstraint = b
     for cls, (pa, gs) in saved.items():
         cls.process_action, cls.grad_steps = pa, gs
         if "exact_loop_exit" in cls.__dict__:

@@ -531,9 +531,13 @@ class Gen(object):
         e("// Reduced correction direction = EVOPFEnv.ineq_partial_grad (evopf.py:596-612) in two-solve form")
         e("// (SURVEY App. B.4) on the 22x22 Newton block (28x28 J_O is block triangular, SURVEY H3).")
         e("// Also evaluates the loop test of grad_steps (rpo_ddpg.py:271-272): *eqmax = max|eq_resid|, *ineqmax = max ineq_dist.")
-        e("// post-factor part of the direction: d = sign-of-violation vector (43), lu/ipiv = factors of the Newton block at y")
-        e("RPO_HD void evopf_direction_post(const real* y, const EvopfPt& pt, const real* lu, const real* ipiv, const real* d, real* out) {")
-        e("    real rhs[EVOPF_NN], tL[6], tP[14], tQ[14], cs[6], q[28];")
+        e("// post-factor part of the direction: d = sign-of-violation vector (43), lu/ipiv = factors of the Newton block at y.")
+        e("// Split around its plain solve so that the fused projection loop can share ONE inlined copy of evopf_solve between")
+        e("// the Newton iteration and the correction step:  pre (transposed solve, g_P, rhs = -q_N) -> evopf_solve -> fin.")
+        e("// keep[22] = [q_L(6) | gpg(5) | gpe(5) | gvm(5) | gva0] carries the values fin needs across the solve.")
+        e("#define EVOPF_DIRKEEP 22")
+        e("RPO_HD void evopf_direction_pre(const real* y, const EvopfPt& pt, const real* lu, const real* ipiv, const real* d, real* rhs, real* keep) {")
+        e("    real tL[6], tP[14], tQ[14], cs[6], q[28];")
         e("    tL[0] = d[%d];" % (K.PG0 + 0))
         for gi in range(K.NG):
             e("    tL[%d] = d[%d];" % (1 + gi, K.QG0 + gi))
@@ -581,34 +585,48 @@ class Gen(object):
                     self.accum(tgt, terms, init=init, negate=True)
         for k, (kind, i) in enumerate(self.eqs):
             e("    rhs[%d] = -q[%d];" % (k, i if kind == "P" else 14 + i))
-        e("    evopf_solve(lu, ipiv, rhs);")
-        # u_s = q_L + F[L, w] u~ ; out_O = -u
         Lrows = self.L_rows()
+        for li, row in enumerate(Lrows):
+            e("    keep[%d] = q[%d];" % (li, row[1] if row[0] == "P" else 14 + row[1]))
+        for gi in range(5):
+            e("    keep[%d] = gpg[%d]; keep[%d] = gpe[%d]; keep[%d] = gvm[%d];" % (6 + gi, gi, 11 + gi, gi, 16 + gi, gi))
+        e("    keep[21] = gva0;")
+        e("}")
+        e("")
+        e("RPO_HD void evopf_direction_fin(const real* y, const EvopfPt& pt, const real* rhs, const real* keep, real* out) {")
+        # u_s = q_L + F[L, w] u~ ; out_O = -u
         Lout = [K.PG0 + 0] + [K.QG0 + gi for gi in range(K.NG)]
+        assert len(Lrows) == 6
         for li, row in enumerate(Lrows):
             terms = []
             for c, unk in enumerate(self.unk):
                 f = self.F(row, unk)
                 if f is not None:
                     terms.append((f, "rhs[%d]" % c))
-            qidx = row[1] if row[0] == "P" else 14 + row[1]
             e("    {")
             e("    real u_;")
-            self.accum("u_", terms, init="q[%d]" % qidx)
+            self.accum("u_", terms, init="keep[%d]" % li)
             e("    out[%d] = -u_;" % Lout[li])
             e("    }")
         for gidx in K.PV_:
-            e("    out[%d] = gpg[%d];" % (K.PG0 + int(gidx), int(gidx)))
+            e("    out[%d] = keep[%d];" % (K.PG0 + int(gidx), 6 + int(gidx)))
         for gi, b in enumerate(self.spv):
-            e("    out[%d] = gvm[%d];" % (K.VM0 + b, gi))
-        e("    out[%d] = gva0;" % (K.VA0 + self.slack))
+            e("    out[%d] = keep[%d];" % (K.VM0 + b, 16 + gi))
+        e("    out[%d] = keep[21];" % (K.VA0 + self.slack))
         for gi in range(K.NE):
-            e("    out[%d] = gpe[%d];" % (K.PE0 + gi, gi))
+            e("    out[%d] = keep[%d];" % (K.PE0 + gi, 11 + gi))
         for c, (kind, j) in enumerate(self.unk):
             if kind == "th":
                 e("    out[%d] = -rhs[%d];" % (K.VA0 + j, c))
             else:
                 e("    out[%d] = -(y[%d] * rhs[%d]);" % (K.VM0 + j, K.VM0 + j, c))
+        e("}")
+        e("")
+        e("RPO_HD void evopf_direction_post(const real* y, const EvopfPt& pt, const real* lu, const real* ipiv, const real* d, real* out) {")
+        e("    real rhs[EVOPF_NN], keep[EVOPF_DIRKEEP];")
+        e("    evopf_direction_pre(y, pt, lu, ipiv, d, rhs, keep);")
+        e("    evopf_solve(lu, ipiv, rhs);")
+        e("    evopf_direction_fin(y, pt, rhs, keep, out);")
         e("}")
         e("")
         e("RPO_HD real evopf_direction(const real* x, const real* pe_max, const real* pe_min, const real* y, real* out, real* eqmax, real* ineqmax) {")
@@ -649,7 +667,7 @@ def op_stats(txt):
         per[name] = dict(fma=fma, mul=mul, add=add, flop=2 * fma + mul + add)
     fl = lambda *names: sum(per[n]["flop"] for n in names)
     newton = fl("evopf_eval_full", "evopf_newton_rhs", "evopf_factor", "evopf_solve", "evopf_newton_update")
-    post = fl("evopf_direction_post", "evopf_rhs_t", "evopf_solve_t", "evopf_colsums", "evopf_solve")
+    post = fl("evopf_direction_pre", "evopf_direction_fin", "evopf_rhs_t", "evopf_solve_t", "evopf_colsums", "evopf_solve")
     corr = fl("evopf_eval_full", "evopf_eq_resid", "evopf_ineq", "evopf_factor") + post + 2 * 43
     bwd = fl("evopf_eval_full", "evopf_factor", "evopf_rhs_t", "evopf_solve_t", "evopf_colsums", "evopf_backward")
     return dict(per_function=per, newton_iter_flop=newton, corr_step_flop=corr, tail_flop=fl("evopf_tail"),
