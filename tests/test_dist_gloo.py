@@ -37,17 +37,24 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.timeout(120)
+def _free_port():
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.timeout(600)
 def test_flat_bucket_allreduce_equals_single_process_gradient():
-    world, port = 2, 29517 + os.getpid() % 200
+    world, port = 2, _free_port()                                    # generous timeouts: a loaded CI host spawns slowly
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted([q.get(timeout=100) for _ in range(world)], key=lambda t: t[0])
+    res = sorted([q.get(timeout=500) for _ in range(world)], key=lambda t: t[0])
     for p in procs:
-        p.join(timeout=30)
+        p.join(timeout=60)
         assert p.exitcode == 0
     (_, f0, fl0, w0, s0), (_, f1, fl1, w1, s1) = res
     assert torch.equal(w0, w1), "broadcast_parameters must equalise the replicas"
