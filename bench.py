@@ -191,6 +191,10 @@ def main():
     dev = torch.device("cuda", local_rank)
     import torch.distributed as dist
     if world > 1:
+        # NCCL may print its version banner on fd 1 (NCCL_DEBUG=VERSION on some boxes): stdout must carry the JSON line only
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
         # NCCL builds its communicator lazily at the first collective (hundreds of ms with the GPU idle): do it here,
         # not at the barrier that opens the timed region — the idle GPU would drop its clocks and the first ~50 ms of
@@ -199,6 +203,9 @@ def main():
         dist.all_reduce(warm)
         dist.barrier()
         torch.cuda.synchronize()
+        sys.stdout.flush()
+        os.dup2(saved_fd, 1)
+        os.close(saved_fd)
 
     B = 1 << args.log2_batch
     # each rank owns its own contiguous shard of the global batch (seeded per rank); no data-path collective

@@ -1,14 +1,16 @@
 #!/usr/bin/env python
-"""Data-parallel RPO-DDPG on EVOPF-v0 with the B200 projection path (BASELINE.json configs[3]-style run).
+"""Data-parallel RPO-DDPG / RPO-SAC on EVOPF-v0 with the B200 projection path (BASELINE.json configs[2] / configs[3]).
 
-  python examples/train_evopf_dp.py                                   # 1 GPU
-  python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 examples/train_evopf_dp.py
+  python examples/train_evopf_dp.py                                   # 1 GPU, DDPG
+  python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 examples/train_evopf_dp.py --algo sac --graph
 
 Every rank owns `--envs` EVOPF replicas stepped on the GPU (rpo_b200.vector) and a device-resident replay buffer;
 the projection (completion + correction, GRG backward) runs with NO communication; the only collective is ONE
 all-reduce of the flat actor / critic gradient bucket per optimiser step (rpo_b200.dist.FlatGradBucket).
 The update rules follow rpo/algo/rpo_ddpg.py:163-205,307-337 (critic smooth-L1 on the projected target action,
-actor loss -Q + nju . ineq_dist through complete_partial, soft target update, dual ascent on nju).
+actor loss -Q + nju . ineq_dist through complete_partial, soft target update, dual ascent on nju) or, with --algo sac,
+rpo/algo/rpo_sac.py:167-219,322-355 with the tanh-Gaussian policy of rpo/algo/model/policy.py:34-66 (twin critics,
+entropy term alpha * log_pi with the box's action_scale in the log-density, automatic temperature).
 This is a harness around the hot path, not a re-implementation of the reference's agent layer.
 """
 from __future__ import annotations
@@ -58,6 +60,7 @@ def main():
     ap.add_argument("--corr-lr", type=float, default=1e-4)
     ap.add_argument("--max-steps", type=int, default=10)
     ap.add_argument("--policy-fre", type=int, default=4)
+    ap.add_argument("--algo", choices=("ddpg", "sac"), default="ddpg")
     ap.add_argument("--graph", action="store_true", help="capture the training iteration in CUDA graphs (SURVEY f-3)")
     a = ap.parse_args()
     rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -70,26 +73,43 @@ def main():
     proj = Projector(env, a)
     venv = EvopfVectorEnv(a.envs, dev, seed=rank, default_generator=a.graph)
     box = BoxConstraint(*env.box_constraint_partial, device=dev, volatile=env.volatile, update=env.update)
-    actor, critic = mlp(57, 14).to(dev), mlp(57 + 43, 1).to(dev)
-    actor_t, critic_t = mlp(57, 14).to(dev), mlp(57 + 43, 1).to(dev)
+    sac = a.algo == "sac"
+    n_q = 2 if sac else 1                               # twin critics as one network with two outputs (rpo_sac.py:344-352)
+    actor, critic = mlp(57, 28 if sac else 14).to(dev), mlp(57 + 43, n_q).to(dev)
+    actor_t, critic_t = mlp(57, 28 if sac else 14).to(dev), mlp(57 + 43, n_q).to(dev)
+    log_alpha = torch.zeros(1, device=dev, requires_grad=True)
+    target_entropy = -14.0
     nju = nn.Linear(58, 1, bias=False).to(dev)
     nn.init.zeros_(nju.weight)
     broadcast_parameters([actor, critic, nju])
     actor_t.load_state_dict(actor.state_dict())
     critic_t.load_state_dict(critic.state_dict())
     b_critic = FlatGradBucket(critic.parameters())
-    b_actor = FlatGradBucket(list(actor.parameters()) + list(nju.parameters()))
+    b_actor = FlatGradBucket(list(actor.parameters()) + list(nju.parameters()) + ([log_alpha] if sac else []))
     opt_c = torch.optim.Adam(critic.parameters(), lr=3e-4, capturable=a.graph)
     opt_a = torch.optim.Adam(actor.parameters(), lr=1e-4, capturable=a.graph)
     opt_n = torch.optim.Adam(nju.parameters(), lr=2e-2, maximize=True, capturable=a.graph)
+    opt_al = torch.optim.Adam([log_alpha], lr=3e-4, capturable=a.graph)
     replay = DeviceReplay(a.envs * 64, dev, default_generator=a.graph, state=57, action=43, next_state=57, reward=1, done=1)
 
     def policy(net, s, noise=0.0):
         """box(tanh(net(s)), s) with the state-dependent battery bounds: ONE launch of rpo_box_fwd (f-1; policy.py:30-31)."""
+        if sac:
+            return sample(net, s)[0]
         if not noise:
             return box.squash(net(s), s)
         u = torch.tanh(net(s))
         return box((u + noise * torch.randn_like(u)).clamp(-1, 1), s)
+
+    def sample(net, s):
+        """tanh-Gaussian policy (policy.py:48-64): returns (partial action in the box, log_pi (B,1))."""
+        mean, log_std = net(s).split(14, dim=1)
+        log_std = (log_std - 3).clamp(-20, 2)
+        u = mean + log_std.exp() * torch.randn_like(mean)
+        y = torch.tanh(u)
+        logp = -0.5 * ((u - mean) / log_std.exp()) ** 2 - log_std - 0.9189385332046727
+        logp = logp - torch.log(box.action_scale(s) * (1 - y.pow(2)) + 1e-6)
+        return box(y, s), logp.sum(1, keepdim=True)
 
     venv.reset()
     last_rew = torch.zeros(a.envs, device=dev)
@@ -106,11 +126,18 @@ def main():
             last_rew.copy_(rew)
         smp = replay.sample(a.batch)
         hold["state"] = smp["state"]
-        with torch.no_grad():                           # critic target (rpo_ddpg.py:327-332)
-            na = proj.process_action(smp["next_state"], policy(actor_t, smp["next_state"]))
-            tq = smp["reward"] + 0.95 * (1 - smp["done"]) * critic_t(torch.cat([smp["next_state"], na], 1))
+        with torch.no_grad():                           # critic target (rpo_ddpg.py:327-332 / rpo_sac.py:340-347)
+            if sac:
+                nz, nlogp = sample(actor, smp["next_state"])
+                na = proj.process_action(smp["next_state"], nz)
+                nq = critic_t(torch.cat([smp["next_state"], na], 1)).min(dim=1, keepdim=True).values - log_alpha.exp() * nlogp
+            else:
+                na = proj.process_action(smp["next_state"], policy(actor_t, smp["next_state"]))
+                nq = critic_t(torch.cat([smp["next_state"], na], 1))
+            tq = smp["reward"] + 0.95 * (1 - smp["done"]) * nq
         b_critic.zero_()
-        F.smooth_l1_loss(critic(torch.cat([smp["state"], smp["action"]], 1)), tq).backward()
+        q = critic(torch.cat([smp["state"], smp["action"]], 1))
+        F.smooth_l1_loss(q, tq.expand_as(q), reduction="sum").div(q.shape[0]).backward()
 
     def seg_critic_step(do_actor: bool):
         """Critic optimiser step (+ actor forward/backward through the GRG kernel); ends at the actor all-reduce."""
@@ -118,13 +145,23 @@ def main():
         if do_actor:                                    # actor loss (rpo_ddpg.py:307-324)
             b_actor.zero_()
             s = hold["state"]
-            act_c = env.complete_partial(s, policy(actor, s))          # autograd: GRG backward kernel
-            loss = (-critic(torch.cat([s, act_c], 1)) + nju(env.ineq_dist(s, act_c))).mean()
+            if sac:                                     # rpo_sac.py:322-338
+                zs, logp = sample(actor, s)
+                act_c = env.complete_partial(s, zs)                    # autograd: GRG backward kernel
+                qmin = critic(torch.cat([s, act_c], 1)).min(dim=1, keepdim=True).values
+                loss = (log_alpha.exp().detach() * logp - qmin + nju(env.ineq_dist(s, act_c))).mean()
+                # automatic temperature (rpo_sac.py:207-214); its gradient rides in the actor bucket's all-reduce
+                loss = loss - (log_alpha * (logp.detach() + target_entropy)).mean()
+            else:
+                act_c = env.complete_partial(s, policy(actor, s))          # autograd: GRG backward kernel
+                loss = (-critic(torch.cat([s, act_c], 1)) + nju(env.ineq_dist(s, act_c))).mean()
             loss.backward()
 
     def seg_actor_step():
         opt_a.step()                                    # rpo_ddpg.py:199-205
         opt_n.step()
+        if sac:
+            opt_al.step()
         with torch.no_grad():
             nju.weight.clamp_(min=0)
             for t, o in ((actor_t, actor), (critic_t, critic)):
@@ -191,7 +228,7 @@ def main():
         n_all = float(n_proj)
     if rank == 0:
         print(json.dumps({"world": world, "iters": a.iters, "envs_per_gpu": a.envs, "batch_per_gpu": a.batch,
-                          "cuda_graph": bool(a.graph), "iters_per_s": a.iters / dt, "projected_actions_per_s": n_all / dt,
+                          "algo": a.algo, "cuda_graph": bool(a.graph), "iters_per_s": a.iters / dt, "projected_actions_per_s": n_all / dt,
                           "env_steps_per_s": world * a.envs * a.iters / dt, "max_replica_drift": float(drift.item()),
                           "final_reward_mean": float(rew.mean()), "finite": bool(torch.isfinite(w).all())}))
     if world > 1:
