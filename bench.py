@@ -314,6 +314,10 @@ def main():
     # end-to-end through the host-buffer API: pinned host inputs -> H2D -> kernels -> D2H results, every step
     e2e = None
     if not args.no_e2e:
+        bound = False
+        if world > 1 and os.environ.get("RPO_BIND_NUMA", "1") != "0":
+            from rpo_b200.host_api import bind_host_thread_to_device
+            bound = bind_host_thread_to_device(dev)           # pinned buffers below land in the GPU's NUMA node
         hp = HostProjector(dev, chunk=1 << 17, n_streams=4, corr_lr=CORR["lr"], momentum=CORR["momentum"],
                            corr_eps=CORR["corr_eps"], n_steps=CORR["n_steps"], **NEWTON)
         pst, pz, pg = st_h.pin_memory(), z_h.pin_memory(), g_h.pin_memory()
@@ -333,6 +337,7 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * B * e2e_steps / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": hp.h2d_bytes,
                "d2h_bytes_per_step": hp.d2h_bytes, "steps": e2e_steps, "chunk": hp.chunk, "streams": len(hp.streams),
+               "host_thread_bound_to_gpu_numa": bound,
                "max_abs_diff_vs_resident": float((yc_out.to(dev) - out[0]).abs().max())}
 
     if rank != 0:
