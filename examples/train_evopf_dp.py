@@ -139,9 +139,16 @@ def main():
         q = critic(torch.cat([smp["state"], smp["action"]], 1))
         F.smooth_l1_loss(q, tq.expand_as(q), reduction="sum").div(q.shape[0]).backward()
 
+    def soft_update(pairs, tau=0.005):
+        with torch.no_grad():
+            for t, o in pairs:
+                torch._foreach_lerp_(list(t.parameters()), list(o.parameters()), tau)
+
     def seg_critic_step(do_actor: bool):
         """Critic optimiser step (+ actor forward/backward through the GRG kernel); ends at the actor all-reduce."""
         opt_c.step()
+        if sac:                                         # SAC: the critic target moves every step (rpo_sac.py:219)
+            soft_update(((critic_t, critic),))
         if do_actor:                                    # actor loss (rpo_ddpg.py:307-324)
             b_actor.zero_()
             s = hold["state"]
@@ -164,9 +171,8 @@ def main():
             opt_al.step()
         with torch.no_grad():
             nju.weight.clamp_(min=0)
-            for t, o in ((actor_t, actor), (critic_t, critic)):
-                for pt, po in zip(t.parameters(), o.parameters()):
-                    pt.lerp_(po, 0.005)
+        if not sac:                                     # DDPG: targets move on actor-update steps only (rpo_ddpg.py:205)
+            soft_update(((actor_t, actor), (critic_t, critic)))
 
     def iteration(do_actor: bool, run=None):
         """Three segments separated by the two collectives, which always run eagerly (capturing NCCL collectives inside
