@@ -100,6 +100,22 @@ def test_fused_equals_separate_and_backward_linearity(data):
     assert float(err.max()) <= 1e-3 and float(err.median()) <= 1e-5
 
 
+def test_pipelined_backward_equals_one_pass_kernel(data):
+    """Large aligned batches take the persistent double-buffered backward kernel (k_evopf_bwd_pipe); small batches and
+    the ragged remainder take the one-pass kernel.  Same per-instance code: the results must be bit-equal."""
+    from rpo_b200 import ops
+    n = B - 51                                              # 8191 full tiles + a 77-row remainder
+    y, g = data["y"][:n], data["g_d"][:n]
+    for need_dx in (False, True):
+        dz, dx = ops.evopf_complete_bwd(y, g, need_dx=need_dx)
+        C = 1 << 14                                         # 128 tiles per call: below the persistent kernel's threshold
+        parts = [ops.evopf_complete_bwd(y[b0:b0 + C], g[b0:b0 + C], need_dx=need_dx) for b0 in range(0, n, C)]
+        assert torch.equal(dz, torch.cat([p[0] for p in parts]))
+        if need_dx:
+            assert torch.equal(dx, torch.cat([p[1] for p in parts]))
+    assert torch.equal(data["dz"][:n], dz)
+
+
 def test_correction_is_idempotent_on_feasible_points(data):
     """rpo_ddpg.py:271: one step is always taken, but it is a zero step where no inequality is violated."""
     from rpo_b200 import ops
