@@ -24,7 +24,7 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
-METRIC = "RPO projected actions/sec (completion+correction, fwd+bwd)"
+METRIC = "RPO projected actions/sec (completion+correction, fwd+bwd) at 1/2/4/8 B200"      # BASELINE.json "metric", verbatim
 UNIT = "projected actions/s"
 LOG2_B = 20
 CORR = dict(lr=1e-4, momentum=0.0, corr_eps=1e-5, n_steps=10)      # scripts/evopf_exp.py:29-31
