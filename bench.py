@@ -404,9 +404,52 @@ def main():
         "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * args.steps * world,
         "roofline": roofline, "cpu_baseline": cpu_baseline, "wall_s_timed_region": t_wall,
     }
+    if world == 1:
+        line["other_configs"] = classic_configs(dev)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def classic_configs(dev):
+    """BASELINE.json configs[0] / configs[1] on the GPU (reported beside the headline, same metric): closed-form completion +
+    10 correction steps fused (`rpo_*_project`) + completion backward, 2^24 instances resident, reference settings
+    (scripts/cart_exp.py, scripts/pen_exp.py: corr_lr 2e-2 / 2e-3), CUDA events over 20 steps after 3 warm-up steps."""
+    import torch
+    from rpo_b200 import ops, synth
+    n = 1 << 24
+    out = {}
+
+    def timed(step):
+        for _ in range(3):
+            step()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(20):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 20
+
+    g = synth.upstream_grad(n, 2, seed=5, device=dev)
+    _, z = synth.cart_inputs(n, seed=1, device=dev)
+
+    def cart_step():
+        ops.cart_project(z, 1, 2e-2, 0.0, 1e-5, 10, want_a=True)
+        ops.cart_complete_bwd(g, 1)
+    ms = timed(cart_step)
+    out["safe_cartpole"] = {"workload": "CartSafe-v0 completion+correction (fwd+bwd), 2^24 instances", "value": n / (ms * 1e-3),
+                            "unit": UNIT, "ms_per_step": ms, "bytes_per_instance": 40}
+    obs, zp = synth.pen_inputs(n, seed=2, device=dev)
+
+    def pen_step():
+        ops.pen_project(obs, zp, 2e-3, 0.0, 1e-5, 10, want_a=True)
+        ops.pen_complete_bwd(obs, g)
+    ms = timed(pen_step)
+    out["spring_pendulum"] = {"workload": "SpringPendulum-v0 completion+correction (fwd+bwd), 2^24 instances", "value": n / (ms * 1e-3),
+                              "unit": UNIT, "ms_per_step": ms, "bytes_per_instance": 88}
+    return out
 
 
 if __name__ == "__main__":

@@ -47,4 +47,6 @@ def test_product_arm_line():
     assert e["value"] < d["value"]                                     # host buffers cross PCIe inside the timed region
     c = d["cpu_baseline"]
     assert c["kind"] == "port" and c["value"] > 0 and c["cores"] >= 1
+    o = d["other_configs"]                                             # BASELINE.json configs[0] / configs[1] beside the headline
+    assert o["safe_cartpole"]["value"] > 1e9 and o["spring_pendulum"]["value"] > 1e9
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
