@@ -153,3 +153,22 @@ def test_fused_single_loop_equals_complete_then_correct(libs):
                          ctypes.c_float(0.5), ctypes.c_float(1e-5), 7, _P(flags2), _P(status2))
     assert np.array_equal(y, y2) and np.array_equal(yc, yc2)
     assert np.array_equal(status, status2) and np.array_equal(flags, flags2)
+
+
+@pytest.mark.parametrize("scale", [0.4, 1.0, 1.5])
+def test_load_scale_sweep(scale, evopf_oracle):
+    """Far outside the synthetic distribution (40 % ... 150 % of the nominal load): the generated Newton completion keeps
+    tracking the oracle on every instance it reports as converged, and reports the others in the status word."""
+    from rpo_b200 import synth
+    from tests import hostsim_ops as hs
+    B = 384
+    st = synth.evopf_states(B, seed=int(scale * 100))
+    st[:, :28] *= scale
+    z = synth.evopf_partial_actions(st, seed=7, dist="D1")
+    y_h, status = hs.evopf_complete_fwd(st, z, return_status=True)
+    y_o = evopf_oracle.complete_partial_fwd(st, z)
+    conv = ((status >> 8) == 0) & torch.isfinite(y_o).all(dim=1)
+    assert int(conv.sum()) >= B - 2                      # at most a couple of infeasible power flows at 150 %
+    rel = (y_h - y_o).abs().max(dim=1).values / y_o.abs().max(dim=1).values
+    assert float(rel[conv].max()) <= Y_RTOL / 5
+    assert int((status[conv] & 0xFF).max()) <= 7
