@@ -27,5 +27,7 @@ t_py = timeit(lambda: ops.evopf_project(st, z, 1e-4, 0.0, 1e-5, 10, want_y=True)
 t_d = timeit(lambda: ops.evopf_direction(st, y))
 t_r = timeit(lambda: ops.evopf_resid(st, y))
 print('B %d  fwd %.3f  corr %.3f  bwd %.3f  project %.3f  project+y %.3f  direction %.3f resid %.3f ms' % (B, t_f, t_c, t_b, t_p, t_py, t_d, t_r))
+t_nf = timeit(lambda: ops.evopf_project(st, z, 1e-4, 0.0, 1e-5, 10, want_flags=False))
+print('project without flag buffer %.3f ms (with: %.3f)' % (t_nf, t_p))
 yc = ops.evopf_project(st, z, 1e-4, 0.0, 1e-5, 10)[0]
 print('projected actions/s (project+y + bwd): %.4g  checksum %.10f' % (B/((t_py+t_b)*1e-3), float(yc.double().sum())))
