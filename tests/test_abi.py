@@ -71,3 +71,54 @@ def test_missing_library_is_an_error(built, monkeypatch):
     monkeypatch.setattr(built, "LIB_PATH", "/nonexistent/librpo_b200.so")
     with pytest.raises(built.RpoLibraryError):
         built.load()
+
+
+def _prototypes():
+    """name -> list of C parameter types, parsed from the header."""
+    hdr = open(os.path.join(ROOT, "include", "rpo_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = {}
+    for ret, name, args in re.findall(r"\b(int|const char\*)\s+(rpo_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr):
+        args = " ".join(args.split())
+        params = [] if args in ("", "void") else [a.strip() for a in args.split(",")]
+        protos[name] = (ret, [re.sub(r"\s*\b[A-Za-z_][A-Za-z0-9_]*$", "", p).strip() for p in params])
+    return protos
+
+
+def test_ctypes_signatures_match_the_header(built):
+    """Every row of the ctypes table has the header's arity and a compatible type in every position."""
+    import ctypes
+    kinds = {"int": ctypes.c_int, "int64_t": ctypes.c_int64, "float": ctypes.c_float}
+    protos = _prototypes()
+    assert sorted(protos) == sorted(built.SIGNATURES)
+    for name, (ret, params) in protos.items():
+        restype, argtypes = built.SIGNATURES[name]
+        assert restype is (ctypes.c_int if ret == "int" else ctypes.c_char_p), name
+        assert len(argtypes) == len(params), (name, params, argtypes)
+        for c_type, ct in zip(params, argtypes):
+            if "*" in c_type:
+                assert ct is ctypes.c_void_p, (name, c_type)
+            else:
+                assert ct is kinds[c_type], (name, c_type, ct)
+
+
+def test_generated_header_is_up_to_date(tmp_path):
+    """rpo_b200/csrc/evopf_gen.cuh is committed; it must be exactly what tools/gen_evopf.py emits today."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_evopf", os.path.join(ROOT, "tools", "gen_evopf.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    txt = gen.Gen().generate()
+    assert txt == open(os.path.join(ROOT, "rpo_b200", "csrc", "evopf_gen.cuh")).read()
+
+
+def test_box_argument_validation_without_gpu(built):
+    lib = built.load()
+    P = 1                                                     # any non-null pointer value: rejected before it is used
+    assert lib.rpo_box_fwd(P, P, P, 14, P, 57, 5, P, 9, 4, None) == -1 and b"mode" in lib.rpo_last_error()
+    assert lib.rpo_box_fwd(P, P, P, 14, P, 57, 3, P, 0, 4, None) == -1 and b"n_vol" in lib.rpo_last_error()
+    assert lib.rpo_box_fwd(P, P, P, 14, None, 57, 5, P, 0, 4, None) == -1          # volatile box without soc
+    assert lib.rpo_box_fwd(P, P, P, 0, None, 0, 0, P, 0, 4, None) == -1            # width
+    assert lib.rpo_box_fwd(None, P, P, 14, P, 57, 5, P, 0, 4, None) == -1          # x missing for an x-mode
+    assert lib.rpo_box_bwd(P, P, P, P, 14, P, 57, 5, P, 4, 4, None) == -1          # no backward for the query modes
+    assert lib.rpo_box_fwd(P, P, P, 14, P, 57, 5, P, 0, 0, None) == 0              # empty batch
