@@ -172,3 +172,21 @@ def test_load_scale_sweep(scale, evopf_oracle):
     rel = (y_h - y_o).abs().max(dim=1).values / y_o.abs().max(dim=1).values
     assert float(rel[conv].max()) <= Y_RTOL / 5
     assert int((status[conv] & 0xFF).max()) <= 7
+
+
+@pytest.mark.parametrize("K,mom,lr", [(50, 0.5, 1e-4), (50, 0.0, 5e-4)])
+def test_long_correction_and_momentum(K, mom, lr, evopf_oracle):
+    """eval-length loops (eval_steps = 50, rpo_ddpg.py:288-305), momentum and a 5x larger step: the generated correction
+    step stays on the oracle's trajectory (mask flips aside)."""
+    from oracle.rpo_oracle import grad_steps
+    from rpo_b200 import synth
+    from tests import hostsim_ops as hs
+    B = 64
+    st = synth.evopf_states(B, seed=77)
+    z = synth.evopf_partial_actions(st, seed=78)
+    y = evopf_oracle.complete_partial_fwd(st, z)
+    yc_o, k = grad_steps(evopf_oracle, st, y, lr, mom, 1e-5, K)
+    yc_h, flags = hs.evopf_correct(st, y, lr, mom, 1e-5, K)
+    assert k == K and flags.tolist() == [1] * K
+    rel = (yc_h - yc_o).abs().max(dim=1).values / yc_o.abs().max(dim=1).values
+    assert float(rel.median()) <= 1e-6 and int((rel > Y_RTOL).sum()) <= 1
