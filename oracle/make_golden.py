@@ -211,11 +211,26 @@ def box():
     np.savez(os.path.join(OUT, "box.npz"), **out)
 
 
+def pen_batched():
+    """The reference's BATCHED pendulum calls (rows coupled through the (B,B) product, pendulum.py:337-339): direction and
+    RPODDPG.grad_steps on the whole batch of tests/golden/pen.npz at once.  Pins the opt-in reference_batch_coupling mode."""
+    rpo = load_reference()
+    env = make_cpu_env("pen")
+    gs = rpo.algo.RPODDPG.grad_steps
+    g = np.load(os.path.join(OUT, "pen.npz"))
+    obs, a = torch.tensor(g["obs"]), torch.tensor(g["a"])
+    out = {"dir": env.ineq_partial_grad(obs, a).numpy()}
+    out["a_corr"] = gs(_Algo(env, 2e-3, 10), obs, a, train=True).numpy()
+    ace, k = gs(_Algo(env, 2e-3, 10, momentum=0.5, eval_steps=50), obs, a, train=False)
+    out["a_corr_eval_momentum"], out["eval_steps"] = ace.numpy(), np.array(k)
+    np.savez(os.path.join(OUT, "pen_batched.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
-    which = sys.argv[1:] or ["evopf", "cart", "pen", "box"]
+    which = sys.argv[1:] or ["evopf", "cart", "pen", "box", "pen_batched"]
     for name in which:
-        {"evopf": evopf, "cart": cart, "pen": pen, "box": box}[name]()
+        {"evopf": evopf, "cart": cart, "pen": pen, "box": box, "pen_batched": pen_batched}[name]()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

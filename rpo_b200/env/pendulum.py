@@ -4,6 +4,12 @@ Row-wise semantics: the reference's batched ineq_partial_grad multiplies (B,1) b
 couples rows for B > 1; every kernel here evaluates a row as the reference evaluates a batch of one.
 The reference caches diff_eq* on the env between calls (pendulum.py:264-288); the kernels recompute them from the
 observation (5 flops), so this class is stateless between protocol calls.
+
+`reference_batch_coupling=True` (opt-in) reproduces the reference's batched behaviour literally instead: the correction
+direction of row i then sums the reduced gradients d_j of ALL rows j with a_p[i] d_j > b_i (the (B,B) product), and
+`correct` / `project` run the reference's loop step by step around it.  That path is a handful of torch operations
+(O(B^2) like the reference's), not a kernel: it exists so that a batched call can be compared with the reference
+result for result; the row-wise kernels stay the default and the fast path.
 """
 from __future__ import annotations
 
@@ -29,7 +35,8 @@ class _CompleteFn(torch.autograd.Function):
 class SpringPendulumEnv(object):
     metadata = {"render_modes": ["human", "rgb_array"], "render_fps": 30}
 
-    def __init__(self, g=10.0, device=None):
+    def __init__(self, g=10.0, device=None, reference_batch_coupling=False):
+        self.reference_batch_coupling = bool(reference_batch_coupling)
         self.max_speed, self.max_torque, self.max_length_delta = 8.0, 6.0, 0.5
         self.max_summation = 32.0
         self.dt, self.g, self.m, self.k, self.l0 = 0.05, g, 0.5, 1.0, 1.0
@@ -79,7 +86,38 @@ class SpringPendulumEnv(object):
         return torch.clamp(self.ineq_resid(state, action), 0)
 
     def ineq_partial_grad(self, state, action, eps=0):
+        if self.reference_batch_coupling and action.shape[0] > 1:
+            return self._direction_coupled(state, action)
         return ops.pen_direction(state, action)
+
+    def _direction_coupled(self, state, action, rows_per_block: int = 4096):
+        """pendulum.py:331-343 for a batch, operation for operation (float32): row i is coupled to every row j through
+        `action[:, p] @ diff_grad_partial.T` (B,1)@(1,B).  Evaluated in row blocks to bound the (B,B) temporary."""
+        cos, sin, thd, l, ld = (state[:, i:i + 1] for i in range(5))
+        e_p, inv_o = sin, 1 / cos                                              # diff_eq_partial, diff_eq_other_inv (:273-281)
+        bias = -self.m_dt * ld - (l * self.m * thd ** 2 - self.k * (l - self.l0) - self.m * self.g * cos)      # :287
+        D = 2 * action.detach()                                                # set_ineq :294
+        d = D[:, 0:1] - D[:, 1:2] * (inv_o * e_p)                              # diff_grad_partial :334-335
+        b = self.max_summation - (bias * inv_o) * D[:, 1:2]                    # bias_grad_partial :336
+        grad = torch.empty_like(d)
+        for r0 in range(0, action.shape[0], rows_per_block):
+            m = torch.clamp(action[r0:r0 + rows_per_block, 0:1] @ d.T - b[r0:r0 + rows_per_block], 0)     # :337
+            grad[r0:r0 + rows_per_block] = (m > 0).to(torch.float32) @ d                                  # :339
+        return torch.cat([grad, -(grad * e_p) * inv_o], dim=1)                 # :340-342
+
+    def _correct_coupled(self, state, action, lr, momentum, corr_eps, n_steps):
+        """RPODDPG.grad_steps (rpo_ddpg.py:266-286) step by step, always n_steps steps like the kernels; flags[k] = the
+        reference's loop test before step k."""
+        a = action.detach().clone()
+        prev = torch.zeros_like(a)
+        flags = torch.zeros(max(n_steps, 1), dtype=torch.int32, device=a.device)
+        for k in range(n_steps):
+            unsat = (self.eq_resid(state, a).abs().max() > corr_eps) | (self.ineq_dist(state, a).max() > corr_eps)
+            flags[k] = unsat.to(torch.int32)
+            step = lr * self._direction_coupled(state, a) + momentum * prev
+            a = a - step
+            prev = step
+        return a, flags
 
     def ineq_dist_np(self, state, action):
         return self.ineq_dist(self._t(state), self._t(action)).cpu().numpy()
@@ -88,10 +126,16 @@ class SpringPendulumEnv(object):
         return self.eq_resid(self._t(state), self._t(action)).cpu().numpy()
 
     def correct(self, state, action, lr, momentum, corr_eps, n_steps):
+        if self.reference_batch_coupling and action.shape[0] > 1:
+            return self._correct_coupled(state, action, lr, momentum, corr_eps, n_steps)
         return ops.pen_correct(state, action, lr, momentum, corr_eps, n_steps)
 
     def project(self, state, action_partial, lr, momentum, corr_eps, n_steps):
         z = action_partial.view(-1, 1) if action_partial.dim() == 1 else action_partial
+        if self.reference_batch_coupling and z.shape[0] > 1:
+            a = ops.pen_complete_fwd(state, z)
+            ac, flags = self._correct_coupled(state, a, lr, momentum, corr_eps, n_steps)
+            return ac, a, flags
         ac, a, flags = ops.pen_project(state, z, lr, momentum, corr_eps, n_steps, want_a=True)
         return ac, a, flags
 
