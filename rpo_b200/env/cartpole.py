@@ -93,6 +93,45 @@ class CartSafeEnv(object):
     def eq_resid_np(self, state, action):
         return self.eq_resid(None, self._t(action)).cpu().numpy()[0]
 
+    def ineq_resid_np(self, state, action):                       # cartpole.py:410-411
+        return self.ineq_resid(None, self._t(action)).cpu().numpy()[0]
+
+    def eq_dist_np(self, state, action):                          # cartpole.py:420-422
+        return np.abs(self.eq_resid_np(state, action))
+
+    # Penalty-gradient forms used only by corr_mode != 0 (rpo_ddpg.py:275-278; no reference script): two tiny torch
+    # products over the constant constraint matrices, kept for protocol completeness (cartpole.py:389-394).
+    def _constraint_matrices(self, device):
+        if getattr(self, "_mats", None) is None or self._mats[0].device != device:
+            delta = torch.tensor([np.pi / 3, -np.pi / 6], dtype=torch.float32, device=device)
+            E = torch.sin(delta).view(1, 2)
+            A = torch.cat([torch.cos(delta).view(1, 2), -torch.cos(delta).view(1, 2),
+                           torch.tensor([[1.0, 0.0], [-1.0, 0.0], [0.0, 1.0], [0.0, -1.0]], device=device)], dim=0)
+            self._mats = (E, A)
+        return self._mats
+
+    def eq_grad(self, state, action):
+        E, _ = self._constraint_matrices(action.device)
+        return 2 * (action @ E.T) @ E
+
+    def ineq_grad(self, state, action):
+        _, A = self._constraint_matrices(action.device)
+        return 2 * self.ineq_dist(state, action) @ A
+
+    # The reference caches nothing for this environment either; the hold / release switches exist for API parity
+    # (cartpole.py:424-434).
+    def hold_eq(self):
+        self.holding_eq = True
+
+    def release_eq(self):
+        self.holding_eq = False
+
+    def hold_ineq(self):
+        self.holding_ineq = True
+
+    def release_ineq(self):
+        self.holding_ineq = False
+
     def correct(self, state, action, lr, momentum, corr_eps, n_steps):
         return ops.cart_correct(action, self._p, lr, momentum, corr_eps, n_steps)
 

@@ -119,6 +119,7 @@ class EVOPFEnv(object):
     neq = property(lambda self: self._neq)
     nineq = property(lambda self: self._nineq)
     nknowns = property(lambda self: self._nknowns)
+    partial_unknown_vars = property(lambda self: np.concatenate([K.PG0 + K.PV_, K.VM0 + K.SPV]))      # evopf.py:291,474
     device = property(lambda self: self._device)
 
     @property
@@ -136,6 +137,19 @@ class EVOPFEnv(object):
         else:
             t = torch.as_tensor(np.asarray(a), dtype=torch.float32, device=self._device)
         return t.view(1, -1) if t.dim() == 1 else t
+
+    def decompose(self, state):                                 # evopf.py:454-455
+        return state[:2 * self.nbus], state[2 * self.nbus:]
+
+    def obj_fn(self, action):                                   # evopf.py:509-518 (float64 result: genbase is a float64 array there)
+        """Generation cost of `action` (the reward of `step` is computed inside rpo_evopf_step; this method is the
+        reference's stand-alone helper, a few torch operations)."""
+        pg = self._t(action)[:, :self.ng].double()
+        pg_mw = pg * torch.as_tensor(self.genbase, dtype=torch.float64, device=pg.device)
+        quad = torch.as_tensor(K.QUAD_COSTS, dtype=torch.float32, device=pg.device).double()
+        lin = torch.as_tensor(K.LIN_COSTS, dtype=torch.float32, device=pg.device).double()
+        cost = (quad * pg_mw ** 2).sum(dim=1) + (lin * pg_mw).sum(dim=1) + K.CONST_COST
+        return cost / (float(np.mean(self.genbase)) ** 2)
 
     def get_action_vars(self, action):                          # evopf.py:501-507
         return (action[:, :self.ng], action[:, self.ng:2 * self.ng], action[:, 2 * self.ng:2 * self.ng + self.nbus],

@@ -125,6 +125,26 @@ class SpringPendulumEnv(object):
     def eq_resid_np(self, state, action):
         return self.eq_resid(self._t(state), self._t(action)).cpu().numpy()
 
+    # The reference caches diff_eq* / diff_ineq on the env and lets callers freeze them (pendulum.py:264-296, 345-355);
+    # the kernels recompute them from the observation, so these are switches without effect, kept for API parity.
+    def set_eq(self, state, action_partial=None):
+        return None
+
+    def set_ineq(self, state, action):
+        return None
+
+    def hold_eq(self):
+        self.holding_eq = True
+
+    def release_eq(self):
+        self.holding_eq = False
+
+    def hold_ineq(self):
+        self.holding_ineq = True
+
+    def release_ineq(self):
+        self.holding_ineq = False
+
     def correct(self, state, action, lr, momentum, corr_eps, n_steps):
         if self.reference_batch_coupling and action.shape[0] > 1:
             return self._correct_coupled(state, action, lr, momentum, corr_eps, n_steps)
