@@ -16,8 +16,12 @@ def _stream(t: torch.Tensor) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
+def _is_device_tensor(t) -> bool:
+    return isinstance(t, torch.Tensor) and t.is_cuda
+
+
 def _dev(t: torch.Tensor, name: str, cols: Optional[int] = None) -> torch.Tensor:
-    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+    if not _is_device_tensor(t):
         raise _lib.RpoLibraryError("%s must be a CUDA tensor (rpo_b200 has no CPU path)" % name)
     if t.dtype != torch.float32:
         raise TypeError("%s must be float32, got %s" % (name, t.dtype))
@@ -30,7 +34,7 @@ def _dev(t: torch.Tensor, name: str, cols: Optional[int] = None) -> torch.Tensor
 
 def _rows(t: torch.Tensor, name: str, min_cols: int) -> Tuple[torch.Tensor, int]:
     """A (B, S>=min_cols) float32 CUDA tensor whose rows are contiguous; returns (tensor, leading dimension)."""
-    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+    if not _is_device_tensor(t):
         raise _lib.RpoLibraryError("%s must be a CUDA tensor (rpo_b200 has no CPU path)" % name)
     if t.dtype != torch.float32:
         raise TypeError("%s must be float32, got %s" % (name, t.dtype))
@@ -46,6 +50,13 @@ def _rows(t: torch.Tensor, name: str, min_cols: int) -> Tuple[torch.Tensor, int]
     return t, t.stride(0)
 
 
+def _same_batch(B: int, **tensors) -> None:
+    """Every row-wise argument must carry the batch size the kernel is launched with: the kernels index raw pointers."""
+    for name, t in tensors.items():
+        if t is not None and t.shape[0] != B:
+            raise ValueError("%s has %d rows, expected %d" % (name, t.shape[0], B))
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
@@ -56,8 +67,7 @@ def evopf_complete_fwd(state, z, tol: float = 1e-5, max_iters: int = 50, return_
     state, ld = _rows(state, "state", 28)
     z = _dev(z, "z", 14)
     B = z.shape[0]
-    if state.shape[0] != B:
-        raise ValueError("state and z disagree on the batch size")
+    _same_batch(B, state=state)
     y = torch.empty(B, 43, dtype=torch.float32, device=z.device)
     status = torch.empty(B, dtype=torch.int32, device=z.device) if return_status else None
     with torch.cuda.device(z.device):
@@ -71,6 +81,7 @@ def evopf_complete_bwd(y, dl_dy, need_dx: bool = True):
     y = _dev(y, "y", 43)
     dl_dy = _dev(dl_dy, "dl_dy", 43)
     B = y.shape[0]
+    _same_batch(B, dl_dy=dl_dy)
     dz = torch.empty(B, 14, dtype=torch.float32, device=y.device)
     dx = torch.empty(B, 28, dtype=torch.float32, device=y.device) if need_dx else None
     with torch.cuda.device(y.device):
@@ -84,6 +95,7 @@ def evopf_direction(state, y):
     state, ld = _rows(state, "state", 33)
     y = _dev(y, "y", 43)
     B = y.shape[0]
+    _same_batch(B, state=state)
     out = torch.empty_like(y)
     with torch.cuda.device(y.device):
         _lib.check(lib.rpo_evopf_direction(state.data_ptr(), ld, y.data_ptr(), out.data_ptr(), B, _stream(y)),
@@ -96,6 +108,7 @@ def evopf_correct(state, y, lr: float, momentum: float, corr_eps: float, n_steps
     state, ld = _rows(state, "state", 33)
     y = _dev(y, "y", 43)
     B = y.shape[0]
+    _same_batch(B, state=state)
     out = torch.empty_like(y)
     flags = torch.empty(max(n_steps, 1), dtype=torch.int32, device=y.device) if want_flags else None
     with torch.cuda.device(y.device):
@@ -110,6 +123,7 @@ def evopf_project(state, z, lr: float, momentum: float, corr_eps: float, n_steps
     state, ld = _rows(state, "state", 33)
     z = _dev(z, "z", 14)
     B = z.shape[0]
+    _same_batch(B, state=state)
     y = torch.empty(B, 43, dtype=torch.float32, device=z.device) if want_y else None
     yc = torch.empty(B, 43, dtype=torch.float32, device=z.device)
     flags = torch.empty(max(n_steps, 1), dtype=torch.int32, device=z.device) if want_flags else None
@@ -126,6 +140,7 @@ def evopf_resid(state, y, want_eq: bool = True, want_ineq: bool = True):
     state, ld = _rows(state, "state", 33)
     y = _dev(y, "y", 43)
     B = y.shape[0]
+    _same_batch(B, state=state)
     eq = torch.empty(B, 28, dtype=torch.float32, device=y.device) if want_eq else None
     ineq = torch.empty(B, 58, dtype=torch.float32, device=y.device) if want_ineq else None
     with torch.cuda.device(y.device):
@@ -140,6 +155,7 @@ def evopf_step(state, y, next_exo, want_viol: bool = True):
     y = _dev(y, "y", 43)
     next_exo = _dev(next_exo, "next_exo", 52)
     B = y.shape[0]
+    _same_batch(B, state=state, next_exo=next_exo)
     ns = torch.empty(B, 57, dtype=torch.float32, device=y.device)
     rew = torch.empty(B, dtype=torch.float32, device=y.device)
     eqv = torch.empty(B, 28, dtype=torch.float32, device=y.device) if want_viol else None
@@ -221,6 +237,7 @@ def cart_step(state, a, want_viol=True):
     state = _dev(state, "state", 6)
     a = _dev(a, "a", 2)
     B = a.shape[0]
+    _same_batch(B, state=state)
     ns = torch.empty(B, 6, dtype=torch.float32, device=a.device)
     done = torch.empty(B, dtype=torch.int32, device=a.device)
     eqv = torch.empty(B, 1, dtype=torch.float32, device=a.device) if want_viol else None
@@ -237,6 +254,7 @@ def pen_complete_fwd(obs, z):
     obs = _dev(obs, "obs", 5)
     z = _dev(z, "z", 1)
     B = z.shape[0]
+    _same_batch(B, obs=obs)
     a = torch.empty(B, 2, dtype=torch.float32, device=z.device)
     with torch.cuda.device(z.device):
         _lib.check(lib.rpo_pen_complete_fwd(obs.data_ptr(), z.data_ptr(), a.data_ptr(), B, _stream(z)), "rpo_pen_complete_fwd")
@@ -248,6 +266,7 @@ def pen_complete_bwd(obs, dl_da):
     obs = _dev(obs, "obs", 5)
     dl_da = _dev(dl_da, "dl_da", 2)
     B = dl_da.shape[0]
+    _same_batch(B, obs=obs)
     dz = torch.empty(B, 1, dtype=torch.float32, device=dl_da.device)
     with torch.cuda.device(dl_da.device):
         _lib.check(lib.rpo_pen_complete_bwd(obs.data_ptr(), dl_da.data_ptr(), dz.data_ptr(), B, _stream(dl_da)),
@@ -259,6 +278,7 @@ def pen_direction(obs, a):
     lib = _lib.load()
     obs = _dev(obs, "obs", 5)
     a = _dev(a, "a", 2)
+    _same_batch(a.shape[0], obs=obs)
     out = torch.empty_like(a)
     with torch.cuda.device(a.device):
         _lib.check(lib.rpo_pen_direction(obs.data_ptr(), a.data_ptr(), out.data_ptr(), a.shape[0], _stream(a)), "rpo_pen_direction")
@@ -269,6 +289,7 @@ def pen_correct(obs, a, lr, momentum, corr_eps, n_steps, want_flags=True):
     lib = _lib.load()
     obs = _dev(obs, "obs", 5)
     a = _dev(a, "a", 2)
+    _same_batch(a.shape[0], obs=obs)
     out = torch.empty_like(a)
     flags = torch.empty(max(n_steps, 1), dtype=torch.int32, device=a.device) if want_flags else None
     with torch.cuda.device(a.device):
@@ -282,6 +303,7 @@ def pen_project(obs, z, lr, momentum, corr_eps, n_steps, want_a=False, want_flag
     obs = _dev(obs, "obs", 5)
     z = _dev(z, "z", 1)
     B = z.shape[0]
+    _same_batch(B, obs=obs)
     a = torch.empty(B, 2, dtype=torch.float32, device=z.device) if want_a else None
     ac = torch.empty(B, 2, dtype=torch.float32, device=z.device)
     flags = torch.empty(max(n_steps, 1), dtype=torch.int32, device=z.device) if want_flags else None
@@ -296,6 +318,7 @@ def pen_resid(obs, a, want_eq=True, want_ineq=True):
     obs = _dev(obs, "obs", 5)
     a = _dev(a, "a", 2)
     B = a.shape[0]
+    _same_batch(B, obs=obs)
     eq = torch.empty(B, 1, dtype=torch.float32, device=a.device) if want_eq else None
     ineq = torch.empty(B, 1, dtype=torch.float32, device=a.device) if want_ineq else None
     with torch.cuda.device(a.device):
@@ -308,6 +331,7 @@ def pen_step(st, a, want_viol=True):
     st = _dev(st, "st", 4)
     a = _dev(a, "a", 2)
     B = a.shape[0]
+    _same_batch(B, st=st)
     dev = a.device
     nst = torch.empty(B, 4, dtype=torch.float32, device=dev)
     nobs = torch.empty(B, 5, dtype=torch.float32, device=dev)
@@ -365,6 +389,7 @@ def box_bwd(x, grad_out, lo, hi, mode: int = BOX_AFFINE, state=None, n_vol: int 
     lib = _lib.load()
     x, lo, hi, W, state, soc_ptr, ld, B = _box_args(x, lo, hi, state, n_vol, mode, None)
     g = _dev(grad_out, "grad_out", W)
+    _same_batch(B, grad_out=g)
     gx = torch.empty(B, W, dtype=torch.float32, device=lo.device)
     with torch.cuda.device(lo.device):
         _lib.check(lib.rpo_box_bwd(x.data_ptr(), g.data_ptr(), lo.data_ptr(), hi.data_ptr(), W, soc_ptr, ld, n_vol, gx.data_ptr(),
