@@ -84,6 +84,7 @@ class EVOPFEnv(object):
                                   curve=price_curve, pickle_path=pp)                      # evopf.py:216
         self.nbus, self.ng, self.ne = K.NBUS, K.NG, K.NE
         self._box_dev = {}
+        self._ineq_jac = {}
         self.genbase, self.baseMVA = K.GENBASE.copy(), K.BASE_MVA
         self.slack, self.pv, self.spv, self.pq = K.SLACK.copy(), K.PV.copy(), K.SPV.copy(), K.PQ.copy()
         self.slack_, self.pv_, self.spv_ = K.SLACK_.copy(), K.PV_.copy(), K.SPV_.copy()
@@ -177,13 +178,30 @@ class EVOPFEnv(object):
         """The constant +-1 selector `ineq_jac` (evopf.py:663-707) is never built: the product is the sign-of-violation
         vector, assembled on the device from the residual kernel's output."""
         m = (self.ineq_resid(state, action) > 0).to(torch.float32)
+        return self._fold_ineq_rows(m)
+
+    def _fold_ineq_rows(self, w):
+        """ineq_jac^T . w for a (B,58) weight on the inequality rows: the selector has one +1 (upper bound) and one -1
+        (lower bound) per bounded variable, so the product is a difference of column blocks."""
         ng, nb = self.ng, self.nbus
-        d = torch.zeros(action.shape[0], self.ydim, dtype=torch.float32, device=action.device)
-        d[:, 0:ng] = m[:, 0:ng] - m[:, ng:2 * ng]
-        d[:, ng:2 * ng] = m[:, 2 * ng:3 * ng] - m[:, 3 * ng:4 * ng]
-        d[:, 2 * ng:2 * ng + nb] = m[:, 4 * ng:4 * ng + nb] - m[:, 4 * ng + nb:4 * ng + 2 * nb]
-        d[:, -self.ne:] = m[:, 4 * ng + 2 * nb:5 * ng + 2 * nb] - m[:, 5 * ng + 2 * nb:]
+        d = torch.zeros(w.shape[0], self.ydim, dtype=w.dtype, device=w.device)
+        d[:, 0:ng] = w[:, 0:ng] - w[:, ng:2 * ng]
+        d[:, ng:2 * ng] = w[:, 2 * ng:3 * ng] - w[:, 3 * ng:4 * ng]
+        d[:, 2 * ng:2 * ng + nb] = w[:, 4 * ng:4 * ng + nb] - w[:, 4 * ng + nb:4 * ng + 2 * nb]
+        d[:, -self.ne:] = w[:, 4 * ng + 2 * nb:5 * ng + 2 * nb] - w[:, 5 * ng + 2 * nb:]
         return d
+
+    def ineq_grad(self, state, action, eps=0.0):                # evopf.py:584-588 (corr_mode != 0 only)
+        dist = self.ineq_dist(state, action)
+        return 2 * self._fold_ineq_rows(dist + (dist > 0) * eps)
+
+    def ineq_jac(self, state, action):                          # evopf.py:663-707: constant (58,43) selector, expanded
+        key = str(action.device)
+        if key not in self._ineq_jac:
+            eye = torch.eye(self.ineq_num, dtype=torch.float32, device=action.device)
+            self._ineq_jac[key] = self._fold_ineq_rows(eye).contiguous()          # row r = ineq_jac[r, :]
+        jac = self._ineq_jac[key]
+        return jac.unsqueeze(0).expand(action.shape[0], *jac.shape)
 
     def ineq_dist_np(self, state, action):                      # evopf.py:569-572
         return self.ineq_dist(self._t(state), self._t(action)).cpu().numpy()
@@ -203,10 +221,11 @@ class EVOPFEnv(object):
         return yc, y, flags
 
     def _unsupported(self, *a, **k):
-        raise NotImplementedError("eq_grad / ineq_grad / eq_jac / ineq_jac belong to corr_mode != 0, which no reference "
-                                  "script uses (SURVEY.md §8 a6); the B200 path implements corr_mode == 0")
+        raise NotImplementedError("eq_jac / eq_grad materialise the dense (B,28,43) Jacobian, which the B200 path never builds "
+                                  "(its entries live inside the generated LU); they belong to corr_mode != 0, which no "
+                                  "reference script uses (SURVEY.md §8 a6)")
 
-    eq_grad = ineq_grad = eq_jac = ineq_jac = _unsupported
+    eq_grad = eq_jac = _unsupported
 
     # ---- volatile action box (evopf.py:769-783, Battery.update_bound :127-143) --------------------------
     def update(self, state, full=False):

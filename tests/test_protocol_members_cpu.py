@@ -53,3 +53,22 @@ def test_evopf_members():
     mine, theirs = env.obj_fn(y), ref.obj_fn(y.numpy())
     assert mine.dtype == theirs.dtype == torch.float64
     assert torch.allclose(mine, theirs, rtol=1e-12, atol=0)
+
+
+def test_evopf_ineq_jac_and_grad(monkeypatch):
+    from oracle.ref_loader import make_cpu_env
+    from rpo_b200 import synth
+    from tests import hostsim_ops
+    hostsim_ops.install(monkeypatch)
+    from rpo_b200.env import EVOPFEnv
+    ref = make_cpu_env("evopf")
+    env = EVOPFEnv(device="cpu")
+    st = synth.evopf_states(24, seed=4)
+    lo, hi = env.box_constraint
+    y = torch.from_numpy(lo + (hi - lo) * np.random.default_rng(0).uniform(-0.2, 1.2, size=(24, 43))).float()
+    assert torch.equal(env.ineq_jac(st, y), ref.ineq_jac(st, y))
+    for eps in (0.0, 0.02):
+        assert torch.allclose(env.ineq_grad(st, y, eps=eps), ref.ineq_grad(st, y, eps=eps), rtol=1e-6, atol=1e-6)
+    assert torch.equal(env.ineq_grad_new(st, y), ref.ineq_grad_new(st, y))
+    with pytest.raises(NotImplementedError):
+        env.eq_jac(y)
