@@ -220,12 +220,34 @@ class EVOPFEnv(object):
                                             max_iters=self.newton_max_iters, want_y=True)
         return yc, y, flags
 
-    def _unsupported(self, *a, **k):
-        raise NotImplementedError("eq_jac / eq_grad materialise the dense (B,28,43) Jacobian, which the B200 path never builds "
-                                  "(its entries live inside the generated LU); they belong to corr_mode != 0, which no "
-                                  "reference script uses (SURVEY.md §8 a6)")
+    def eq_jac(self, action):                                   # evopf.py:614-661 -> (B,28,43)
+        """Dense d eq_resid / d action, for inspection and for corr_mode != 0 callers.  The kernels never build it (its
+        entries live inside the generated sparse LU); this is the same branch-term formulation written as a
+        dozen dense torch operations, NOT a hot-path routine: 4.8 KB per instance."""
+        _, _, vm, va, _ = self.get_action_vars(action)
+        dev, dt = action.device, action.dtype
+        G = torch.as_tensor(K.G, dtype=dt, device=dev)
+        Bm = torch.as_tensor(K.B, dtype=dt, device=dev)
+        vr, vi = vm * torch.cos(va), vm * torch.sin(va)
+        al = G * vr[:, None, :] - Bm * vi[:, None, :]                      # alpha_ij, beta_ij: Y_ij (vr_j + j vi_j)
+        be = Bm * vr[:, None, :] + G * vi[:, None, :]
+        T1 = vr[:, :, None] * al + vi[:, :, None] * be
+        T2 = vi[:, :, None] * al - vr[:, :, None] * be
+        P, Q = torch.diag_embed(T1.sum(dim=2)), torch.diag_embed(T2.sum(dim=2))
+        inv_v = (1.0 / vm)[:, None, :]
+        dP_dva, dP_dvm = T2 - Q, (T1 + P) * inv_v
+        dQ_dva, dQ_dvm = P - T1, (T2 + Q) * inv_v
+        n, nb, ng = action.shape[0], self.nbus, self.ng
+        sel = torch.zeros(nb, ng, dtype=dt, device=dev)
+        sel[torch.as_tensor(self.spv, device=dev), torch.arange(ng, device=dev)] = 1.0
+        sel = sel.expand(n, nb, ng)
+        zero = torch.zeros(n, nb, ng, dtype=dt, device=dev)
+        return torch.cat([torch.cat([sel, zero, -dP_dvm, -dP_dva, -sel], dim=2),         # -I for pe: the reference's sign (:639-640)
+                          torch.cat([zero, sel, -dQ_dvm, -dQ_dva, zero], dim=2)], dim=1)
 
-    eq_grad = eq_jac = _unsupported
+    def eq_grad(self, state, action):                           # evopf.py:579-582
+        r = self.eq_resid(state, action)
+        return 2 * self.eq_jac(action).transpose(1, 2).bmm(r.unsqueeze(-1)).squeeze(-1)
 
     # ---- volatile action box (evopf.py:769-783, Battery.update_bound :127-143) --------------------------
     def update(self, state, full=False):

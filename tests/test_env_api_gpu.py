@@ -61,8 +61,9 @@ def test_evopf_env_protocol_and_autograd(evopf_oracle):
     assert np.array_equal(lo, lo_o) and np.array_equal(hi, hi_o)
     lo_d, hi_d = env.update_device(st.cuda())
     assert np.abs(lo_d.cpu().numpy() - lo_o).max() == 0 and np.abs(hi_d.cpu().numpy() - hi_o).max() == 0
-    with pytest.raises(NotImplementedError):
-        env.eq_jac(yd)
+    jac = env.eq_jac(yd)                                     # dense diagnostic form (torch), not a kernel
+    assert jac.shape == (yd.shape[0], 28, 43)
+    assert (jac.cpu() - orc.eq_jac(yd.cpu())).abs().max() < 5e-5
 
 
 def test_process_action_train_and_eval(evopf_oracle):

@@ -70,5 +70,11 @@ def test_evopf_ineq_jac_and_grad(monkeypatch):
     for eps in (0.0, 0.02):
         assert torch.allclose(env.ineq_grad(st, y, eps=eps), ref.ineq_grad(st, y, eps=eps), rtol=1e-6, atol=1e-6)
     assert torch.equal(env.ineq_grad_new(st, y), ref.ineq_grad_new(st, y))
-    with pytest.raises(NotImplementedError):
-        env.eq_jac(y)
+    y[:, 24:38] = (torch.rand(24, 14, generator=torch.Generator().manual_seed(5)) - 0.5) * 0.6        # angles in radians
+    J, Jr = env.eq_jac(y), ref.eq_jac(y)
+    assert J.shape == (24, 28, 43) and float((J - Jr).abs().max()) <= 1e-6 * float(Jr.abs().max())
+    assert torch.allclose(env.eq_grad(st, y), ref.eq_grad(st, y), rtol=1e-4, atol=1e-3)
+    from oracle.rpo_oracle import EvopfOracle
+    J64 = env.eq_jac(y.double())                             # float64 in, float64 out (the reference itself is float32 only)
+    assert J64.dtype == torch.float64
+    assert float((J64 - EvopfOracle(dtype=torch.float64, const_dtype=torch.float32).eq_jac(y.double())).abs().max()) < 1e-5
