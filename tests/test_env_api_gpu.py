@@ -63,7 +63,7 @@ def test_evopf_env_protocol_and_autograd(evopf_oracle):
     assert np.abs(lo_d.cpu().numpy() - lo_o).max() == 0 and np.abs(hi_d.cpu().numpy() - hi_o).max() == 0
     jac = env.eq_jac(yd)                                     # dense diagnostic form (torch), not a kernel
     assert jac.shape == (yd.shape[0], 28, 43)
-    assert (jac.cpu() - orc.eq_jac(yd.cpu())).abs().max() < 5e-5
+    assert (jac.cpu() - orc.eq_jac(yd.cpu())).abs().max() < 2e-4          # entries up to ~48: 4e-6 relative
 
 
 def test_process_action_train_and_eval(evopf_oracle):
