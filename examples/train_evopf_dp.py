@@ -29,7 +29,7 @@ import torch.distributed as dist  # noqa: E402
 import torch.nn as nn  # noqa: E402
 import torch.nn.functional as F  # noqa: E402
 
-from rpo_b200.algo import RPOProjectionMixin  # noqa: E402
+from rpo_b200.algo import RPOProjectionMixin, complete_partial_with_penalty  # noqa: E402
 from rpo_b200.box import BoxConstraint  # noqa: E402
 from rpo_b200.dist import FlatGradBucket, broadcast_parameters  # noqa: E402
 from rpo_b200.env import EVOPFEnv  # noqa: E402
@@ -154,14 +154,15 @@ def main():
             s = hold["state"]
             if sac:                                     # rpo_sac.py:322-338
                 zs, logp = sample(actor, s)
-                act_c = env.complete_partial(s, zs)                    # autograd: GRG backward kernel
+                # autograd: ONE backward kernel for the GRG solve and the nju . ineq_dist penalty (rpo_sac.py:324-334)
+                act_c, pen = complete_partial_with_penalty(env, s, zs, nju.weight)
                 qmin = critic(torch.cat([s, act_c], 1)).min(dim=1, keepdim=True).values
-                loss = (log_alpha.exp().detach() * logp - qmin + nju(env.ineq_dist(s, act_c))).mean()
+                loss = (log_alpha.exp().detach() * logp - qmin + pen).mean()
                 # automatic temperature (rpo_sac.py:207-214); its gradient rides in the actor bucket's all-reduce
                 loss = loss - (log_alpha * (logp.detach() + target_entropy)).mean()
             else:
-                act_c = env.complete_partial(s, policy(actor, s))          # autograd: GRG backward kernel
-                loss = (-critic(torch.cat([s, act_c], 1)) + nju(env.ineq_dist(s, act_c))).mean()
+                act_c, pen = complete_partial_with_penalty(env, s, policy(actor, s), nju.weight)   # rpo_ddpg.py:309-319
+                loss = (-critic(torch.cat([s, act_c], 1)) + pen).mean()
             loss.backward()
 
     def seg_actor_step():

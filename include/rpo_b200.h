@@ -81,6 +81,23 @@ int rpo_evopf_project(const float* state, int ld_state, const float* z, float* y
  * eq (B,28) nullable; ineq (B,58) nullable (ineq_dist = max(ineq, 0)). */
 int rpo_evopf_resid(const float* state, int ld_state, const float* y, float* eq, float* ineq, int64_t B, void* stream);
 
+/* Autograd of EVOPFEnv.eq_resid / ineq_resid / ineq_dist w.r.t. the action   rpo/env/electrical_grid/evopf.py:520-567
+ * The reference's residual functions are plain torch code and its actor loss differentiates through them
+ * (rpo/algo/rpo_ddpg.py:312-319, rpo/algo/rpo_sac.py:326-334: loss += nju(ineq_dist(state, actions))).
+ * dl_dy (B,43) out = (d eq_resid/dy)^T g_eq + (d ineq/dy)^T (g_ineq . m); g_eq (B,28) / g_ineq (B,58) nullable upstream
+ * gradients; ineq_mode 0: ineq_resid (m = 1), 1: ineq_dist = clamp(ineq_resid, 0) (m = [ineq_resid >= 0], torch.clamp's
+ * gradient).  The eq part is the TRUE derivative (+I for pe, evopf.py:532), not eq_jac's -I (evopf.py:639-640). */
+int rpo_evopf_resid_bwd(const float* state, int ld_state, const float* y, const float* g_eq, const float* g_ineq,
+                        int ineq_mode, float* dl_dy, int64_t B, void* stream);
+
+/* PFFunctionFn.backward with the actor loss's inequality penalty folded in  rpo/algo/rpo_ddpg.py:307-324 + evopf.py:857-910
+ * Computes dl_dz / dl_dx of  L(y) + row_scale_b * sum_r w_r * relu(ineq_resid_r(state, y))  given dl_dy = dL/dy:
+ * the +-1 row selector of the violated rows (evopf.py:663-707) is added to dl_dy in registers before the transposed
+ * solve, so the (B,58) ineq_dist gradient is never materialised.  w (58) = Dual.weight (rpo/algo/model/dual.py:47-65);
+ * row_scale (B) nullable (NULL = 1): upstream gradient of the per-row penalty (1/B for loss.mean()). */
+int rpo_evopf_complete_bwd_penalty(const float* state, int ld_state, const float* y, const float* dl_dy, const float* w,
+                                   const float* row_scale, float* dl_dz, float* dl_dx, int64_t B, void* stream);
+
 /* EVOPFEnv.step, batched row-wise                                rpo/env/electrical_grid/evopf.py:348-366 (+Battery.step :74-102, obj_fn :509-518)
  * state (B,57); y (B,43) action; next_exo (B,52) = next [pd|qd](28) + next price window (24) from the data loaders;
  * next_state (B,57) out; reward (B) out; eq_viol (B,28) nullable; ineq_viol (B,58) nullable (both at the pre-step state). */
@@ -105,6 +122,9 @@ int rpo_cart_project(const float* z, float* a, float* a_corr, int64_t B, int par
                      float corr_eps, int n_steps, int32_t* unsat_flags, void* stream);
 /* CartSafeEnv.eq_resid / ineq_resid                              cartpole.py:375-379 ; eq (B,1), ineq (B,6), nullable */
 int rpo_cart_resid(const float* a, float* eq, float* ineq, int64_t B, void* stream);
+/* autograd of CartSafeEnv.eq_resid / ineq_resid / ineq_dist w.r.t. the action   cartpole.py:375-387 (consumed by
+ * rpo_ddpg.py:312-319); g_eq (B,1), g_ineq (B,6) nullable; ineq_mode as rpo_evopf_resid_bwd; a may be NULL when g_ineq is. */
+int rpo_cart_resid_bwd(const float* a, const float* g_eq, const float* g_ineq, int ineq_mode, float* dl_da, int64_t B, void* stream);
 /* CartSafeEnv.step, batched row-wise                             cartpole.py:166-229 ; state (B,6), a (B,2) ->
  * next_state (B,6), done (B) int32, eq_viol (B,1) / ineq_viol (B,6) nullable (unclipped action). */
 int rpo_cart_step(const float* state, const float* a, float* next_state, int32_t* done, float* eq_viol, float* ineq_viol,
@@ -125,6 +145,9 @@ int rpo_pen_project(const float* obs, const float* z, float* a, float* a_corr, i
                     float corr_eps, int n_steps, int32_t* unsat_flags, void* stream);
 /* SpringPendulumEnv.eq_resid / ineq_resid                        pendulum.py:298-303 ; eq (B,1), ineq (B,1), nullable */
 int rpo_pen_resid(const float* obs, const float* a, float* eq, float* ineq, int64_t B, void* stream);
+/* autograd of SpringPendulumEnv.eq_resid / ineq_resid / ineq_dist w.r.t. the action   pendulum.py:296-311 */
+int rpo_pen_resid_bwd(const float* obs, const float* a, const float* g_eq, const float* g_ineq, int ineq_mode, float* dl_da,
+                      int64_t B, void* stream);
 /* SpringPendulumEnv.step, batched row-wise                       pendulum.py:80-128 ; st (B,4) = (th, thdot, l, ldot), a (B,2) ->
  * next_st (B,4), next_obs (B,5), reward (B), done (B) int32, eq_viol (B,1) / ineq_viol (B,1) nullable. */
 int rpo_pen_step(const float* st, const float* a, float* next_st, float* next_obs, float* reward, int32_t* done,

@@ -29,6 +29,8 @@ SIGNATURES = {
     "rpo_evopf_project": (c_int, [_P, c_int, _P, _P, _P, c_int64, c_float, c_int, c_float, c_float, c_float, c_int,
                                   _P, _P, _P]),
     "rpo_evopf_resid": (c_int, [_P, c_int, _P, _P, _P, c_int64, _P]),
+    "rpo_evopf_resid_bwd": (c_int, [_P, c_int, _P, _P, _P, c_int, _P, c_int64, _P]),
+    "rpo_evopf_complete_bwd_penalty": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "rpo_evopf_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "rpo_cart_complete_fwd": (c_int, [_P, _P, c_int64, c_int, _P]),
     "rpo_cart_complete_bwd": (c_int, [_P, _P, c_int64, c_int, _P]),
@@ -36,6 +38,7 @@ SIGNATURES = {
     "rpo_cart_correct": (c_int, [_P, _P, c_int64, c_int, c_float, c_float, c_float, c_int, _P, _P]),
     "rpo_cart_project": (c_int, [_P, _P, _P, c_int64, c_int, c_float, c_float, c_float, c_int, _P, _P]),
     "rpo_cart_resid": (c_int, [_P, _P, _P, c_int64, _P]),
+    "rpo_cart_resid_bwd": (c_int, [_P, _P, _P, c_int, _P, c_int64, _P]),
     "rpo_cart_step": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, _P]),
     "rpo_pen_complete_fwd": (c_int, [_P, _P, _P, c_int64, _P]),
     "rpo_pen_complete_bwd": (c_int, [_P, _P, _P, c_int64, _P]),
@@ -43,6 +46,7 @@ SIGNATURES = {
     "rpo_pen_correct": (c_int, [_P, _P, _P, c_int64, c_float, c_float, c_float, c_int, _P, _P]),
     "rpo_pen_project": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_int, _P, _P]),
     "rpo_pen_resid": (c_int, [_P, _P, _P, _P, c_int64, _P]),
+    "rpo_pen_resid_bwd": (c_int, [_P, _P, _P, _P, c_int, _P, c_int64, _P]),
     "rpo_pen_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "rpo_box_fwd": (c_int, [_P, _P, _P, c_int, _P, c_int, c_int, _P, c_int, c_int64, _P]),
     "rpo_box_bwd": (c_int, [_P, _P, _P, _P, c_int, _P, c_int, c_int, _P, c_int, c_int64, _P]),

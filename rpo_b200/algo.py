@@ -39,6 +39,46 @@ def grad_steps_env(env, state, action, lr: float, momentum: float, corr_eps: flo
     return out, k
 
 
+class _CompletePenaltyFn(torch.autograd.Function):
+    """complete_partial + nju(ineq_dist) of the actor loss (rpo_ddpg.py:309-319) as one autograd node whose backward is
+    ONE kernel (rpo_evopf_complete_bwd_penalty): the penalty's row selector is added to dL/dy in registers before the
+    transposed solve, so neither the (B,58) gradient of ineq_dist nor the sum dL/dy + penalty term exists in HBM."""
+
+    @staticmethod
+    def forward(ctx, state, z, weight, tol, max_iters):
+        from . import ops
+        y = ops.evopf_complete_fwd(state, z, tol=tol, max_iters=max_iters)
+        dist = torch.clamp_(ops.evopf_resid(state, y, want_eq=False, want_ineq=True)[1], 0)
+        ctx.save_for_backward(state, y, dist, weight)
+        return y, dist @ weight.reshape(-1, 1)
+
+    @staticmethod
+    def backward(ctx, dl_dy, dl_dpen):
+        from . import ops
+        state, y, dist, weight = ctx.saved_tensors
+        if dl_dy is None:
+            dl_dy = torch.zeros_like(y)
+        if dl_dpen is None:
+            dl_dpen = torch.zeros(y.shape[0], 1, dtype=y.dtype, device=y.device)
+        dz, dx = ops.evopf_complete_bwd_penalty(state, y, dl_dy.contiguous(), weight.detach(), dl_dpen.contiguous(),
+                                                need_dx=ctx.needs_input_grad[0])
+        d_state = None
+        if ctx.needs_input_grad[0]:
+            d_state = torch.zeros_like(state)
+            d_state[:, :28] = dx
+        d_w = (dl_dpen.reshape(1, -1) @ dist).reshape(weight.shape) if ctx.needs_input_grad[2] else None
+        return d_state, dz, d_w, None, None
+
+
+def complete_partial_with_penalty(env, state, action_partial, nju_weight):
+    """EVOPF: (action, nju(ineq_dist(state, action))) with the fused backward.  Same value and gradients as
+    `a = env.complete_partial(state, z); pen = F.linear(env.ineq_dist(state, a), nju_weight)` (rpo_ddpg.py:309-319,
+    rpo/algo/model/dual.py:63-65), two launches fewer in the backward."""
+    if action_partial.dim() == 1:
+        action_partial = action_partial.view(1, -1)
+    return _CompletePenaltyFn.apply(state, action_partial, nju_weight, env.newton_tol, env.newton_max_iters)
+
+
 class RPOProjectionMixin(object):
     """Mix into (or patch onto) rpo.algo.RPODDPG / RPOSAC: same attribute names, same return conventions."""
 
@@ -50,6 +90,13 @@ class RPOProjectionMixin(object):
         if train:
             a, _ = grad_steps_env(self.env, state, action, self.corr_lr, self.corr_momentum, self.corr_eps,
                                   self.max_steps, self.exact_loop_exit)
+            if torch.is_grad_enabled() and action.requires_grad:
+                # The reference's train-mode loop is differentiable (action - lr * ineq_partial_grad(action),
+                # rpo_ddpg.py:280-281); no reference script differentiates it (the call in actor_loss is commented out,
+                # rpo_ddpg.py:315).  The kernel output carries no graph, so keep the caller's graph alive with a
+                # straight-through estimator: value = corrected action, d/d action = identity, i.e. the correction's
+                # own Jacobian lr * d(direction)/d(action) = O(corr_lr) is dropped.
+                a = action + (a - action).detach()
             return a
         with torch.no_grad():
             return grad_steps_env(self.env, state, action, self.eval_lr, self.corr_momentum, self.corr_eps,

@@ -70,6 +70,23 @@ RPO_HD void cart_resid(const CartK& k, const real* a, real* eq, real* ineq) {
     ineq[5] = -a[1] - RC(10.0);
 }
 
+// autograd of eq_resid (:375-376: bias - a E^T) and ineq_resid / ineq_dist (:378-387: a A^T - b, clamp(., 0)) w.r.t. the
+// action: da = -g_eq E + A^T (g_ineq . m), m = [resid >= 0] for ineq_dist (relu), ones for ineq_resid.  g_eq / g_ineq
+// may be null.  The actor loss differentiates these (rpo_ddpg.py:312-319).
+RPO_HD void cart_resid_vjp(const CartK& k, const real* a, const real* g_eq, const real* g_ineq, int relu, real* da) {
+    real d0 = RC(0.0), d1 = RC(0.0);
+    if (g_eq) { d0 = -(g_eq[0] * k.E[0]); d1 = -(g_eq[0] * k.E[1]); }
+    if (g_ineq) {
+        real eq, iq[6], m[6];
+        cart_resid(k, a, &eq, iq);
+        for (int r = 0; r < 6; ++r) m[r] = (!relu || iq[r] >= RC(0.0)) ? g_ineq[r] : RC(0.0);
+        const real gc = m[0] - m[1];
+        d0 += FMA(gc, k.C[0], m[2] - m[3]);
+        d1 += FMA(gc, k.C[1], m[4] - m[5]);
+    }
+    da[0] = d0; da[1] = d1;
+}
+
 // ineq_partial_grad (:396-408)
 RPO_HD void cart_direction(const CartK& k, const real* a, real* out) {
     const real b[6] = {RC(8.0), RC(8.0), RC(10.0), RC(10.0), RC(10.0), RC(10.0)};
@@ -156,6 +173,20 @@ RPO_HD real pen_complete_bwd(const PenEq& e, const real* da) { return da[0] + (d
 RPO_HD void pen_resid(const PenEq& e, const real* a, real* eq, real* ineq) {
     *eq = e.bias - FMA(a[0], e.ep, a[1] * e.eo);
     *ineq = FMA(a[0], a[0], a[1] * a[1]) - RC(32.0);
+}
+
+// autograd of eq_resid (:296-298: bias - a . [sin, cos]) and ineq_resid / ineq_dist (:300-311: a.a - 32) w.r.t. the action
+RPO_HD void pen_resid_vjp(const PenEq& e, const real* a, const real* g_eq, const real* g_ineq, int relu, real* da) {
+    real d0 = RC(0.0), d1 = RC(0.0);
+    if (g_eq) { d0 = -(g_eq[0] * e.ep); d1 = -(g_eq[0] * e.eo); }
+    if (g_ineq) {
+        real eq, iq;
+        pen_resid(e, a, &eq, &iq);
+        const real m = (!relu || iq >= RC(0.0)) ? g_ineq[0] : RC(0.0);
+        d0 = FMA(RC(2.0) * a[0], m, d0);
+        d1 = FMA(RC(2.0) * a[1], m, d1);
+    }
+    da[0] = d0; da[1] = d1;
 }
 
 RPO_HD void pen_direction(const PenEq& e, const real* a, real* out) {

@@ -73,6 +73,35 @@ RPO_HD bool evopf_correct_step(const real* x, const real* pe_max, const real* pe
     return (eqmax > corr_eps) || (ineqmax > corr_eps);
 }
 
+// Backward of the residual functions w.r.t. the action = what autograd computes for the reference's plain-torch
+// eq_resid / ineq_resid / ineq_dist (evopf.py:520-567), which the actor loss differentiates (rpo_ddpg.py:312-319,
+// rpo_sac.py:326-334):  dy = (d eq_resid/dy)^T g_eq + (d ineq/dy)^T (g_ineq . m),  m = [resid >= 0] for ineq_dist
+// (ineq_mode 1), all ones for ineq_resid (ineq_mode 0).  g_eq / g_ineq may be null.  x = [pd|qd|soc] row.
+RPO_HD void evopf_resid_vjp(const real* x, const real* y, const real* g_eq, const real* g_ineq, int ineq_mode, real* dy) {
+    for (int i = 0; i < 43; ++i) dy[i] = RC(0.0);
+    if (g_eq) {
+        EvopfPt pt;
+        evopf_eval_full(y, pt);
+        evopf_eq_vjp(y, pt, g_eq, g_eq + 14, dy);
+    }
+    if (g_ineq) {
+        real pe_max[5], pe_min[5];
+        evopf_pe_bounds(x + 28, pe_max, pe_min);
+        evopf_ineq_vjp(pe_max, pe_min, y, g_ineq, RC(1.0), ineq_mode, dy);
+    }
+}
+
+// GRG backward with the inequality penalty of the actor loss folded in (rpo_ddpg.py:312-319: loss = -Q + nju(ineq_dist)):
+//   dL/dz, dL/dx of  L(y) + scale * w . relu(ineq_resid(state, y))  given g = dL/dy  — the penalty's +-1 row selector is
+// added to g in registers before the transposed solve, so the (B,58) ineq_dist gradient never exists in HBM.
+RPO_HD real evopf_backward_penalty(const real* soc, const real* y, const real* g, const real* w, real scale, real* dz, real* dx) {
+    real gt[43], pe_max[5], pe_min[5];
+    for (int i = 0; i < 43; ++i) gt[i] = g[i];
+    evopf_pe_bounds(soc, pe_max, pe_min);
+    evopf_ineq_vjp(pe_max, pe_min, y, w, scale, 1, gt);
+    return evopf_backward(y, gt, dz, dx);
+}
+
 // Fused projection = complete_partial followed by n_steps >= 1 correction steps (RPODDPG.process_action,
 // rpo_ddpg.py:72-77) as ONE loop whose body holds a single copy of the two big shared pieces (point evaluation and
 // sparse LU): a Newton iteration and a correction step differ only in what follows the factorisation.  Besides

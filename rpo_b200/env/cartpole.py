@@ -21,6 +21,28 @@ class _CompleteFn(torch.autograd.Function):
         return ops.cart_complete_bwd(dl_da.contiguous(), ctx.partial_idx), None
 
 
+class _ResidFn(torch.autograd.Function):
+    """eq_resid / ineq_resid / ineq_dist with autograd w.r.t. the action, as the reference's torch expressions have
+    (cartpole.py:375-387; differentiated by the actor loss, rpo_ddpg.py:312-319).  kind: 0 eq | 1 ineq_resid | 2 ineq_dist."""
+
+    @staticmethod
+    def forward(ctx, action, kind):
+        ctx.kind = kind
+        ctx.save_for_backward(action)
+        if kind == 0:
+            return ops.cart_resid(action, want_ineq=False)[0]
+        r = ops.cart_resid(action, want_eq=False)[1]
+        return torch.clamp_(r, 0) if kind == 2 else r
+
+    @staticmethod
+    def backward(ctx, g):
+        (action,) = ctx.saved_tensors
+        g = g.contiguous()
+        if ctx.kind == 0:
+            return ops.cart_resid_bwd(action, g_eq=g), None
+        return ops.cart_resid_bwd(action, g_ineq=g, ineq_mode=1 if ctx.kind == 2 else 0), None
+
+
 class CartSafeEnv(object):
     metadata = {"render_modes": ["human", "rgb_array"], "render_fps": 50}
 
@@ -53,6 +75,8 @@ class CartSafeEnv(object):
         self.update = None
         self.action = None
         self.last_state = None
+        self.holding_eq = False                                   # cartpole.py:138-139
+        self.holding_ineq = False
 
     @property
     def _p(self):
@@ -73,16 +97,16 @@ class CartSafeEnv(object):
         return _CompleteFn.apply(z, self._p)
 
     def eq_resid(self, state, action):
-        return ops.cart_resid(action, want_ineq=False)[0]
+        return _ResidFn.apply(action, 0)
 
     def ineq_resid(self, state, action):
-        return ops.cart_resid(action, want_eq=False)[1]
+        return _ResidFn.apply(action, 1)
 
     def eq_dist(self, state, action):
         return torch.abs(self.eq_resid(state, action))
 
     def ineq_dist(self, state, action):
-        return torch.clamp(self.ineq_resid(state, action), 0)
+        return _ResidFn.apply(action, 2)
 
     def ineq_partial_grad(self, state, action, eps=0):
         return ops.cart_direction(action, self._p)

@@ -35,6 +35,39 @@ class _CompleteFn(torch.autograd.Function):
         return dx, dz, None, None
 
 
+class _ResidFn(torch.autograd.Function):
+    """eq_resid / ineq_resid / ineq_dist with the autograd the reference's plain-torch versions have (evopf.py:520-567):
+    the actor loss differentiates through them (rpo_ddpg.py:312-319, rpo_sac.py:326-334).  Forward = rpo_evopf_resid
+    (one launch), backward = rpo_evopf_resid_bwd (one launch; the Jacobian is rebuilt from the action, nothing but
+    (state, action) is saved).  kind: 0 eq_resid | 1 ineq_resid | 2 ineq_dist.  As in the reference, no gradient reaches
+    the state through the inequality rows (the battery bounds pass through numpy, evopf.py:104-121); eq_resid's state
+    gradient is -g on the [pd|qd] columns (:532,:537)."""
+
+    @staticmethod
+    def forward(ctx, state, action, kind):
+        ctx.kind = kind
+        ctx.save_for_backward(state, action)
+        if kind == 0:
+            return ops.evopf_resid(state, action, want_eq=True, want_ineq=False)[0]
+        r = ops.evopf_resid(state, action, want_eq=False, want_ineq=True)[1]
+        return torch.clamp_(r, 0) if kind == 2 else r
+
+    @staticmethod
+    def backward(ctx, g):
+        state, action = ctx.saved_tensors
+        g = g.contiguous()
+        d_state = d_action = None
+        if ctx.needs_input_grad[1]:
+            if ctx.kind == 0:
+                d_action = ops.evopf_resid_bwd(state, action, g_eq=g)
+            else:
+                d_action = ops.evopf_resid_bwd(state, action, g_ineq=g, ineq_mode=1 if ctx.kind == 2 else 0)
+        if ctx.needs_input_grad[0] and ctx.kind == 0:
+            d_state = torch.zeros_like(state)
+            d_state[:, :K.XDIM] = -g
+        return d_state, d_action, None
+
+
 class Battery(object):
     """Host-side bookkeeping of the 5 batteries (evopf.py:23-149); the arithmetic of step / ineq_resid runs in the kernels."""
 
@@ -162,14 +195,14 @@ class EVOPFEnv(object):
             action_partial = action_partial.view(1, -1)
         return _CompleteFn.apply(state[:, :self.xdim], action_partial, self.newton_tol, self.newton_max_iters)
 
-    def eq_resid(self, state, action):                          # evopf.py:520-546
-        return ops.evopf_resid(state, action, want_eq=True, want_ineq=False)[0]
+    def eq_resid(self, state, action):                          # evopf.py:520-546 (differentiable, like the reference's)
+        return _ResidFn.apply(state, action, 0)
 
     def ineq_resid(self, state, action):                        # evopf.py:548-563
-        return ops.evopf_resid(state, action, want_eq=False, want_ineq=True)[1]
+        return _ResidFn.apply(state, action, 1)
 
     def ineq_dist(self, state, action):                         # evopf.py:565-567
-        return torch.clamp(self.ineq_resid(state, action), 0)
+        return _ResidFn.apply(state, action, 2)
 
     def ineq_partial_grad(self, state, action, eps=0.0):        # evopf.py:596-612 (eps is ignored there too)
         return ops.evopf_direction(state, action)

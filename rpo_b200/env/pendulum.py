@@ -32,6 +32,29 @@ class _CompleteFn(torch.autograd.Function):
         return None, ops.pen_complete_bwd(obs, dl_da.contiguous())
 
 
+class _ResidFn(torch.autograd.Function):
+    """eq_resid / ineq_resid / ineq_dist with autograd w.r.t. the action (pendulum.py:296-311; the equality coefficients
+    are detached copies of the observation there, :273-288, so no gradient reaches the state).  kind: 0 | 1 | 2 as in
+    the other environments."""
+
+    @staticmethod
+    def forward(ctx, obs, action, kind):
+        ctx.kind = kind
+        ctx.save_for_backward(obs, action)
+        if kind == 0:
+            return ops.pen_resid(obs, action, want_ineq=False)[0]
+        r = ops.pen_resid(obs, action, want_eq=False)[1]
+        return torch.clamp_(r, 0) if kind == 2 else r
+
+    @staticmethod
+    def backward(ctx, g):
+        obs, action = ctx.saved_tensors
+        g = g.contiguous()
+        if ctx.kind == 0:
+            return None, ops.pen_resid_bwd(obs, action, g_eq=g), None
+        return None, ops.pen_resid_bwd(obs, action, g_ineq=g, ineq_mode=1 if ctx.kind == 2 else 0), None
+
+
 class SpringPendulumEnv(object):
     metadata = {"render_modes": ["human", "rgb_array"], "render_fps": 30}
 
@@ -58,6 +81,8 @@ class SpringPendulumEnv(object):
         self.volatile = False
         self.update = None
         self.state = None
+        self.holding_eq = False                                   # pendulum.py:61-62
+        self.holding_ineq = False
 
     def seed(self, seed=None):
         self.np_random = np.random.RandomState(seed)
@@ -74,16 +99,16 @@ class SpringPendulumEnv(object):
         return _CompleteFn.apply(state, z)
 
     def eq_resid(self, state, action):
-        return ops.pen_resid(state, action, want_ineq=False)[0]
+        return _ResidFn.apply(state, action, 0)
 
     def ineq_resid(self, state, action):
-        return ops.pen_resid(state, action, want_eq=False)[1]
+        return _ResidFn.apply(state, action, 1)
 
     def eq_dist(self, state, action):
         return torch.abs(self.eq_resid(state, action))
 
     def ineq_dist(self, state, action):
-        return torch.clamp(self.ineq_resid(state, action), 0)
+        return _ResidFn.apply(state, action, 2)
 
     def ineq_partial_grad(self, state, action, eps=0):
         if self.reference_batch_coupling and action.shape[0] > 1:

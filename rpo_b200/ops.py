@@ -149,6 +149,42 @@ def evopf_resid(state, y, want_eq: bool = True, want_ineq: bool = True):
     return eq, ineq
 
 
+def evopf_resid_bwd(state, y, g_eq=None, g_ineq=None, ineq_mode: int = 0):
+    """dL/dy of eq_resid / ineq_resid (ineq_mode 0) / ineq_dist (ineq_mode 1) given the upstream gradients (one launch)."""
+    lib = _lib.load()
+    state, ld = _rows(state, "state", 33)
+    y = _dev(y, "y", 43)
+    B = y.shape[0]
+    g_eq = None if g_eq is None else _dev(g_eq, "g_eq", 28)
+    g_ineq = None if g_ineq is None else _dev(g_ineq, "g_ineq", 58)
+    _same_batch(B, state=state, g_eq=g_eq, g_ineq=g_ineq)
+    dy = torch.empty(B, 43, dtype=torch.float32, device=y.device)
+    with torch.cuda.device(y.device):
+        _lib.check(lib.rpo_evopf_resid_bwd(state.data_ptr(), ld, y.data_ptr(), _ptr(g_eq), _ptr(g_ineq), ineq_mode,
+                                           dy.data_ptr(), B, _stream(y)), "rpo_evopf_resid_bwd")
+    return dy
+
+
+def evopf_complete_bwd_penalty(state, y, dl_dy, w, row_scale=None, need_dx: bool = True):
+    """GRG backward of L(y) + row_scale * w . relu(ineq_resid(state, y)) in one launch (the actor loss of rpo_ddpg.py:307-324)."""
+    lib = _lib.load()
+    state, ld = _rows(state, "state", 33)
+    y = _dev(y, "y", 43)
+    dl_dy = _dev(dl_dy, "dl_dy", 43)
+    w = _dev(w, "w", 58)
+    B = y.shape[0]
+    if row_scale is not None:
+        row_scale = _dev(row_scale.reshape(-1, 1), "row_scale", 1)
+    _same_batch(B, state=state, dl_dy=dl_dy, row_scale=row_scale)
+    dz = torch.empty(B, 14, dtype=torch.float32, device=y.device)
+    dx = torch.empty(B, 28, dtype=torch.float32, device=y.device) if need_dx else None
+    with torch.cuda.device(y.device):
+        _lib.check(lib.rpo_evopf_complete_bwd_penalty(state.data_ptr(), ld, y.data_ptr(), dl_dy.data_ptr(), w.data_ptr(),
+                                                      _ptr(row_scale), dz.data_ptr(), _ptr(dx), B, _stream(y)),
+                   "rpo_evopf_complete_bwd_penalty")
+    return dz, dx
+
+
 def evopf_step(state, y, next_exo, want_viol: bool = True):
     lib = _lib.load()
     state = _dev(state, "state", 57)
@@ -230,6 +266,20 @@ def cart_resid(a, want_eq=True, want_ineq=True):
     with torch.cuda.device(a.device):
         _lib.check(lib.rpo_cart_resid(a.data_ptr(), _ptr(eq), _ptr(ineq), B, _stream(a)), "rpo_cart_resid")
     return eq, ineq
+
+
+def cart_resid_bwd(a, g_eq=None, g_ineq=None, ineq_mode: int = 0):
+    lib = _lib.load()
+    a = _dev(a, "a", 2)
+    B = a.shape[0]
+    g_eq = None if g_eq is None else _dev(g_eq, "g_eq", 1)
+    g_ineq = None if g_ineq is None else _dev(g_ineq, "g_ineq", 6)
+    _same_batch(B, g_eq=g_eq, g_ineq=g_ineq)
+    da = torch.empty(B, 2, dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(lib.rpo_cart_resid_bwd(a.data_ptr(), _ptr(g_eq), _ptr(g_ineq), ineq_mode, da.data_ptr(), B, _stream(a)),
+                   "rpo_cart_resid_bwd")
+    return da
 
 
 def cart_step(state, a, want_viol=True):
@@ -324,6 +374,21 @@ def pen_resid(obs, a, want_eq=True, want_ineq=True):
     with torch.cuda.device(a.device):
         _lib.check(lib.rpo_pen_resid(obs.data_ptr(), a.data_ptr(), _ptr(eq), _ptr(ineq), B, _stream(a)), "rpo_pen_resid")
     return eq, ineq
+
+
+def pen_resid_bwd(obs, a, g_eq=None, g_ineq=None, ineq_mode: int = 0):
+    lib = _lib.load()
+    obs = _dev(obs, "obs", 5)
+    a = _dev(a, "a", 2)
+    B = a.shape[0]
+    g_eq = None if g_eq is None else _dev(g_eq, "g_eq", 1)
+    g_ineq = None if g_ineq is None else _dev(g_ineq, "g_ineq", 1)
+    _same_batch(B, obs=obs, g_eq=g_eq, g_ineq=g_ineq)
+    da = torch.empty(B, 2, dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(lib.rpo_pen_resid_bwd(obs.data_ptr(), a.data_ptr(), _ptr(g_eq), _ptr(g_ineq), ineq_mode, da.data_ptr(), B,
+                                         _stream(a)), "rpo_pen_resid_bwd")
+    return da
 
 
 def pen_step(st, a, want_viol=True):

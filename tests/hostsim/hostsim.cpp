@@ -184,5 +184,31 @@ void hs_box_bwd(const real* x, const real* g, const real* lo, const real* hi, in
     hs_box(1, x, g, lo, hi, W, soc, ld_soc, n_vol, gx, mode, B);
 }
 
+void hs_evopf_resid_bwd(const real* state, int ld, const real* y, const real* g_eq, const real* g_ineq, int mode, real* dy, int B) {
+    for (int b = 0; b < B; ++b)
+        evopf_resid_vjp(state + (long)b * ld, y + (long)b * 43, g_eq ? g_eq + (long)b * 28 : (const real*)0,
+                        g_ineq ? g_ineq + (long)b * 58 : (const real*)0, mode, dy + (long)b * 43);
+}
+
+void hs_evopf_backward_penalty(const real* state, int ld, const real* y, const real* g, const real* w, const real* row_scale,
+                               real* dz, real* dx, int B) {
+    for (int b = 0; b < B; ++b)
+        evopf_backward_penalty(state + (long)b * ld + 28, y + (long)b * 43, g + (long)b * 43, w, row_scale ? row_scale[b] : RC(1.0),
+                               dz + (long)b * 14, dx ? dx + (long)b * 28 : (real*)0);
+}
+
+void hs_cart_resid_bwd(const real* a, const real* g_eq, const real* g_ineq, int mode, real* da, int B) {
+    const CartK k = cart_constants(0);
+    for (int b = 0; b < B; ++b)
+        cart_resid_vjp(k, a + 2 * (long)b, g_eq ? g_eq + b : (const real*)0, g_ineq ? g_ineq + 6 * (long)b : (const real*)0, mode,
+                       da + 2 * (long)b);
+}
+
+void hs_pen_resid_bwd(const real* obs, const real* a, const real* g_eq, const real* g_ineq, int mode, real* da, int B) {
+    for (int b = 0; b < B; ++b)
+        pen_resid_vjp(pen_set_eq(obs + 5 * (long)b), a + 2 * (long)b, g_eq ? g_eq + b : (const real*)0,
+                      g_ineq ? g_ineq + b : (const real*)0, mode, da + 2 * (long)b);
+}
+
 int hs_sizeof_real() { return (int)sizeof(real); }
 }

@@ -208,6 +208,45 @@ def pen_step(st, a, want_viol=True):
     return _t(nst), _t(nobs), _t(rew), _t(done), (eq if want_viol else None), (torch.clamp(iq, 0) if want_viol else None)
 
 
+def evopf_resid_bwd(state, y, g_eq=None, g_ineq=None, ineq_mode=0):
+    s, yy = _np(state), _np(y, 43)
+    B = yy.shape[0]
+    ge = None if g_eq is None else _np(g_eq, 28)
+    gi = None if g_ineq is None else _np(g_ineq, 58)
+    dy = np.zeros((B, 43), np.float32)
+    lib().hs_evopf_resid_bwd(_P(s), s.shape[1], _P(yy), _P(ge), _P(gi), ineq_mode, _P(dy), B)
+    return _t(dy)
+
+
+def evopf_complete_bwd_penalty(state, y, dl_dy, w, row_scale=None, need_dx=True):
+    s, yy, g = _np(state), _np(y, 43), _np(dl_dy, 43)
+    B = yy.shape[0]
+    ww = _np(w, 58).reshape(-1)
+    rs = None if row_scale is None else np.ascontiguousarray(_np(row_scale).reshape(-1))
+    dz = np.zeros((B, 14), np.float32)
+    dx = np.zeros((B, 28), np.float32) if need_dx else None
+    lib().hs_evopf_backward_penalty(_P(s), s.shape[1], _P(yy), _P(g), _P(ww), _P(rs), _P(dz), _P(dx), B)
+    return _t(dz), (_t(dx) if need_dx else None)
+
+
+def cart_resid_bwd(a, g_eq=None, g_ineq=None, ineq_mode=0):
+    aa = _np(a, 2)
+    ge = None if g_eq is None else _np(g_eq, 1)
+    gi = None if g_ineq is None else _np(g_ineq, 6)
+    da = np.zeros((aa.shape[0], 2), np.float32)
+    lib().hs_cart_resid_bwd(_P(aa), _P(ge), _P(gi), ineq_mode, _P(da), aa.shape[0])
+    return _t(da)
+
+
+def pen_resid_bwd(obs, a, g_eq=None, g_ineq=None, ineq_mode=0):
+    o, aa = _np(obs, 5), _np(a, 2)
+    ge = None if g_eq is None else _np(g_eq, 1)
+    gi = None if g_ineq is None else _np(g_ineq, 1)
+    da = np.zeros((aa.shape[0], 2), np.float32)
+    lib().hs_pen_resid_bwd(_P(o), _P(aa), _P(ge), _P(gi), ineq_mode, _P(da), aa.shape[0])
+    return _t(da)
+
+
 def _box(bwd, x, g, lo, hi, mode, state, n_vol, B):
     lo_, hi_ = _np(lo).reshape(-1), _np(hi).reshape(-1)
     W = lo_.size

@@ -155,3 +155,88 @@ def test_reference_sac_and_classic_envs_run_on_the_dropin_path(dropin):
             ddpg.run(eval=False)                                     # scripts/cart_exp.py:26-28, scripts/pen_exp.py:26-29
             out = ddpg.eval()                                        # eval(): process_action(train=False) -> (action, step)
         assert ddpg.agent.replay_buffer.size == 30 and np.isfinite(out[0])
+
+
+def _pristine_ddpg():
+    """A fresh RPODDPG class object compiled from the reference file (the fixture has patched the imported one)."""
+    import importlib
+    src = importlib.import_module("rpo.algo.rpo_ddpg")
+    with open(src.__file__) as fh:
+        code = compile(fh.read(), src.__file__, "exec")
+    ns = dict(src.__dict__)
+    from rpo.algo.model.utils import BoxConstraint as RefBox
+    ns["BoxConstraint"] = RefBox                                  # the reference's own host-round-trip box
+    exec(code, ns)
+    return ns["RPODDPG"]
+
+
+def _train_only(algo_a, algo_b, iters):
+    """Run `train(t)` of both algorithm objects on identical replay data, identical RNG streams and identical initial
+    networks; returns the per-iteration max |actor weight difference|."""
+    import copy
+    rb_a, rb_b = algo_a.agent.replay_buffer, algo_b.agent.replay_buffer
+    for k in rb_a.keys:
+        rb_b.buffer[k][...] = rb_a.buffer[k]
+    rb_b.size, rb_b.pointer = rb_a.size, rb_a.pointer
+    for name in ("actor", "critic", "actor_target", "critic_target", "nju", "lamb"):
+        getattr(algo_b.agent, name).load_state_dict(copy.deepcopy(getattr(algo_a.agent, name).state_dict()))
+    for name in ("actor_optim", "critic_optim", "nju_optim", "lamb_optim"):
+        getattr(algo_b.agent, name).load_state_dict(copy.deepcopy(getattr(algo_a.agent, name).state_dict()))
+    algo_b.agent.eps = algo_a.agent.eps
+    flat = lambda al: torch.cat([p.detach().reshape(-1) for p in al.agent.actor.parameters()])
+    drift = []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for t in range(iters):
+            for al in (algo_a, algo_b):
+                np.random.seed(1000 + t)
+                torch.manual_seed(2000 + t)
+                al.train(t)
+            drift.append(float((flat(algo_a) - flat(algo_b)).abs().max()))
+    return drift, flat(algo_a), flat(algo_b)
+
+
+def test_300_train_iterations_with_active_duals_match_reference(dropin, monkeypatch, capsys):
+    """The actor loss's nju . ineq_dist term must reach the actor (rpo_ddpg.py:312-319).  300 reference `train()` calls
+    (75 actor updates) with init_nju = 0.5: (a) all-reference, (b) reference agent on the rpo_b200 path; same replay
+    data, same RNG streams.  The two actors must stay together far tighter than a run whose penalty gradient is cut
+    (the round-1 defect: ineq_dist returned a tensor without grad_fn), which is measured as the negative control."""
+    from oracle.ref_loader import make_cpu_env
+    from rpo_b200.env import EVOPFEnv
+    from rpo_b200.env import evopf as evopf_mod
+    rpo = dropin
+    hp = dict(init_nju=0.5, batch_size=32)
+    RefDDPG = _pristine_ddpg()
+    kw = dict(max_steps=10, warmup=0, lr_dual=2e-2, corr_lr=1e-4, eps=0.0001, eps_start=0.0001, eps_epoch=20000, eval_lr=1e-4,
+              eval_steps=50, grad_eps=0.02, corr_momentum=0.0, policy_fre=4, ex_action_dim=1, gamma=0.95, max_epochs=48,
+              capacity=2000, clip_thres=0.2, shared_param=False, value_type="cat", device=torch.device("cpu"))
+    kw.update(hp)
+    _seed()
+    algo_a = RefDDPG(make_cpu_env("evopf"), "./test", name="t", logger=_Log(), **kw)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        algo_a.run(eval=False)                                       # fills the replay buffer with 48 reference transitions
+    _seed()
+    algo_b = rpo.algo.RPODDPG(EVOPFEnv(device="cpu", data_dir=DATA), "./test", name="t", logger=_Log(), **kw)
+    import copy
+    start = {n: copy.deepcopy(getattr(algo_a.agent, n).state_dict()) for n in ("actor", "critic", "actor_target", "critic_target", "nju")}
+    opt_start = {n: copy.deepcopy(getattr(algo_a.agent, n).state_dict()) for n in ("actor_optim", "critic_optim", "nju_optim", "lamb_optim")}
+    drift, w_a, w_b = _train_only(algo_a, algo_b, 300)
+    moved = float((w_a - torch.cat([p.reshape(-1) for p in start["actor"].values()])).abs().max())
+    assert np.isfinite(drift).all() and moved > 5e-3                  # the actor really trained
+    assert float(algo_a.agent.nju.weight.max()) > 0.0
+    nju_rel = float((algo_a.agent.nju.weight - algo_b.agent.nju.weight).abs().max() / algo_a.agent.nju.weight.abs().max())
+    # negative control: same start, but the drop-in's ineq_dist detached from autograd (round-1 behaviour)
+    for n, sd in start.items():
+        getattr(algo_a.agent, n).load_state_dict(copy.deepcopy(sd))
+    for n, sd in opt_start.items():
+        getattr(algo_a.agent, n).load_state_dict(copy.deepcopy(sd))
+    orig = evopf_mod.EVOPFEnv.ineq_dist
+    monkeypatch.setattr(evopf_mod.EVOPFEnv, "ineq_dist", lambda self, s, a: orig(self, s, a.detach()))
+    drift_cut, _, _ = _train_only(algo_a, algo_b, 300)
+    with capsys.disabled():
+        print("\n[dropin 300 train() iterations, init_nju=0.5] actor moved %.3g; drift vs reference: %.3g (final), "
+              "%.3g (max); with the penalty gradient cut: %.3g; nju rel diff %.3g" % (moved, drift[-1], max(drift), drift_cut[-1], nju_rel))
+    assert max(drift) < 2e-3, max(drift)
+    assert drift_cut[-1] > 5 * max(drift[-1], 1e-5), (drift_cut[-1], drift[-1])
+    assert nju_rel < 1e-2

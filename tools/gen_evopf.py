@@ -526,6 +526,59 @@ class Gen(object):
         e("}")
         e("")
 
+
+    def gen_vjp(self):
+        """Vector-Jacobian products of the two residual functions w.r.t. the action (what torch autograd computes for
+        the reference's plain-torch eq_resid / ineq_resid, evopf.py:520-563) and the GRG backward with the inequality
+        penalty folded in."""
+        e = self.emit
+        e("// dy += (d eq_resid / d y)^T [gP | gQ]  — the TRUE derivative of evopf.py:520-546 (autograd of the torch code):")
+        e("// +I for pe on the P rows (eq_resid adds pe, :532; eq_jac's -I at :639-640 is NOT what autograd sees).")
+        e("// pt must hold evopf_eval_full(y).")
+        e("RPO_HD void evopf_eq_vjp(const real* y, const EvopfPt& pt, const real* gP, const real* gQ, real* dy) {")
+        for g, b in enumerate(self.spv):
+            e("    dy[%d] += gP[%d]; dy[%d] += gQ[%d]; dy[%d] += gP[%d];" % (K.PG0 + g, b, K.QG0 + g, b, K.PE0 + g, b))
+        for j in range(self.nb):
+            for kind in ("th", "V"):
+                terms = []
+                for i in range(self.nb):
+                    fp = self.F(("P", i), (kind, j))
+                    if fp is not None:
+                        terms.append((fp, "gP[%d]" % i))
+                    fq = self.F(("Q", i), (kind, j))
+                    if fq is not None:
+                        terms.append((fq, "gQ[%d]" % i))
+                e("    {")
+                e("    real cs_;")
+                self.accum("cs_", terms)
+                if kind == "th":
+                    e("    dy[%d] -= cs_;" % (K.VA0 + j))
+                else:
+                    e("    dy[%d] -= cs_ / y[%d];" % (K.VM0 + j, K.VM0 + j))
+                e("    }")
+        e("}")
+        e("")
+        e("// dy += (d ineq_resid / d y)^T (g . m): the constant +-1 selector of evopf.py:663-707 applied to the 58 row")
+        e("// gradients g; relu != 0 masks rows by [resid >= 0] (the gradient torch.clamp(resid, 0) passes, evopf.py:565-567).")
+        e("// `scale` multiplies g (per-row weight of a shared dual vector).")
+        e("RPO_HD void evopf_ineq_vjp(const real* pe_max, const real* pe_min, const real* y, const real* g, real scale, int relu, real* dy) {")
+        e("    real hi_, lo_;")
+
+        def pair(yidx, hi, lo, row_hi, row_lo):
+            e("    hi_ = y[%d] - %s; lo_ = %s - y[%d];" % (yidx, hi, lo, yidx))
+            e("    dy[%d] += scale * (((!relu || hi_ >= RC(0.0)) ? g[%d] : RC(0.0)) - ((!relu || lo_ >= RC(0.0)) ? g[%d] : RC(0.0)));"
+              % (yidx, row_hi, row_lo))
+        ng, nb = K.NG, K.NBUS
+        for g in range(ng):
+            pair(K.PG0 + g, lit(K.PMAX_PU[g]), lit(K.PMIN_PU[g]), g, ng + g)
+        for g in range(ng):
+            pair(K.QG0 + g, lit(K.QMAX_PU[g]), lit(K.QMIN_PU[g]), 2 * ng + g, 3 * ng + g)
+        for i in range(nb):
+            pair(K.VM0 + i, lit(K.VMAX_PU[i]), lit(K.VMIN_PU[i]), 4 * ng + i, 4 * ng + nb + i)
+        for g in range(ng):
+            pair(K.PE0 + g, "pe_max[%d]" % g, "pe_min[%d]" % g, 4 * ng + 2 * nb + g, 5 * ng + 2 * nb + g)
+        e("}")
+        e("")
     def gen_direction(self):
         e = self.emit
         e("// Reduced correction direction = EVOPFEnv.ineq_partial_grad (evopf.py:596-612) in two-solve form")
@@ -647,6 +700,7 @@ class Gen(object):
         self.gen_newton()
         self.gen_resid()
         self.gen_backward()
+        self.gen_vjp()
         self.gen_direction()
         return "\n".join(self.out) + "\n"
 
