@@ -1,8 +1,11 @@
 """Import the UNMODIFIED reference (`/root/reference/rpo`) through the stub modules in oracle/stubs.
 
-TEST INFRASTRUCTURE ONLY.  Works only where /root/reference exists (the build container); it is used
-to (i) validate the torch restatement in oracle/rpo_oracle.py and (ii) generate the golden vectors in
-tests/golden/ (oracle/make_golden.py).  Nothing that runs on the GPU box calls this.
+TEST / MEASUREMENT INFRASTRUCTURE ONLY.  In the build container the tree is /root/reference; on the GPU box
+(where that path does not exist) it is the verbatim copy oracle/make_ref_copy.sh placed under oracle/_ref/ (git-ignored,
+shipped by gpurun, SHA-256 list of the original beside it).  Used to (i) validate the torch restatement in
+oracle/rpo_oracle.py, (ii) generate the golden vectors in tests/golden/ (oracle/make_golden.py), (iii) run the reference's
+own RPODDPG / RPOSAC classes over the CUDA kernels in the GPU tests and (iv) time the reference's CPU path as the
+baseline of bench.py.  Nothing under rpo_b200/ imports it.
 """
 from __future__ import annotations
 
@@ -10,13 +13,46 @@ import os
 import sys
 from unittest import mock
 
-REFERENCE_ROOT = os.environ.get("RPO_REFERENCE_ROOT", "/root/reference")
-_STUBS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "stubs")
-_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_STUBS = os.path.join(_HERE, "stubs")
+_REPO = os.path.dirname(_HERE)
+# the verbatim copy oracle/make_ref_copy.sh places for the GPU box (git-ignored, shipped by gpurun)
+REF_COPY = os.path.join(_HERE, "_ref")
+
+
+def _has_tree(root: str) -> bool:
+    return os.path.isfile(os.path.join(root, "rpo", "env", "electrical_grid", "evopf.py"))
+
+
+def _pick_root() -> str:
+    env = os.environ.get("RPO_REFERENCE_ROOT")
+    if env:
+        return env
+    return "/root/reference" if _has_tree("/root/reference") else REF_COPY
+
+
+REFERENCE_ROOT = _pick_root()
+DATA_DIR = os.path.join(REFERENCE_ROOT, "rpo", "env", "electrical_grid", "data", "crawlers")
 
 
 def reference_available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "rpo", "env", "electrical_grid", "evopf.py"))
+    return _has_tree(REFERENCE_ROOT)
+
+
+def verify_copy(root: str = REF_COPY) -> int:
+    """Check every file of a make_ref_copy.sh copy against the SHA-256 list written from the original tree: proves the
+    copy that runs on the GPU box is the unmodified reference.  Returns the number of files checked."""
+    import hashlib
+    n = 0
+    with open(os.path.join(root, "SHA256SUMS")) as fh:
+        for line in fh:
+            digest, rel = line.split(None, 1)
+            rel = rel.strip().lstrip("*")
+            with open(os.path.join(root, rel), "rb") as f:
+                if hashlib.sha256(f.read()).hexdigest() != digest:
+                    raise RuntimeError("reference copy differs from the original: %s" % rel)
+            n += 1
+    return n
 
 
 def load_reference():

@@ -39,6 +39,18 @@ def grad_steps_env(env, state, action, lr: float, momentum: float, corr_eps: flo
     return out, k
 
 
+class _StraightThrough(torch.autograd.Function):
+    """value = `corrected` (bit for bit), gradient = identity to `action` (see RPOProjectionMixin.grad_steps)."""
+
+    @staticmethod
+    def forward(ctx, action, corrected):
+        return corrected.view_as(corrected)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
 class _CompletePenaltyFn(torch.autograd.Function):
     """complete_partial + nju(ineq_dist) of the actor loss (rpo_ddpg.py:309-319) as one autograd node whose backward is
     ONE kernel (rpo_evopf_complete_bwd_penalty): the penalty's row selector is added to dL/dy in registers before the
@@ -96,7 +108,7 @@ class RPOProjectionMixin(object):
                 # rpo_ddpg.py:315).  The kernel output carries no graph, so keep the caller's graph alive with a
                 # straight-through estimator: value = corrected action, d/d action = identity, i.e. the correction's
                 # own Jacobian lr * d(direction)/d(action) = O(corr_lr) is dropped.
-                a = action + (a - action).detach()
+                a = _StraightThrough.apply(action, a)
             return a
         with torch.no_grad():
             return grad_steps_env(self.env, state, action, self.eval_lr, self.corr_momentum, self.corr_eps,

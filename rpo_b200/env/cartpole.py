@@ -7,7 +7,7 @@ import numpy as np
 import torch
 
 from .. import ops
-from .spaces import Box
+from .spaces import Box, EnvBase
 
 
 class _CompleteFn(torch.autograd.Function):
@@ -43,7 +43,7 @@ class _ResidFn(torch.autograd.Function):
         return ops.cart_resid_bwd(action, g_ineq=g, ineq_mode=1 if ctx.kind == 2 else 0), None
 
 
-class CartSafeEnv(object):
+class CartSafeEnv(EnvBase):
     metadata = {"render_modes": ["human", "rgb_array"], "render_fps": 50}
 
     def __init__(self, device=None, partial_idx=None):

@@ -15,7 +15,7 @@ from .. import evopf_constants as K
 from .. import ops
 from ..case14 import case14
 from .loaders import DemandLoader, PriceLoader
-from .spaces import Box
+from .spaces import Box, EnvBase
 
 
 class _CompleteFn(torch.autograd.Function):
@@ -100,14 +100,23 @@ class Battery(object):
         return new_p_max, new_p_min
 
 
-class EVOPFEnv(object):
+class EVOPFEnv(EnvBase):
     metadata = {"render.modes": ["human", "rgb_array"], "video.frames_per_second": 50}
 
     def __init__(self, device=None, demand_curve=None, price_curve=None, data_dir=None):
         self._device = torch.device(device) if device is not None else torch.device("cuda")
         ppc = case14()
         self.ppc = ppc
+        # exogenous series: explicit argument > RPO_EVOPF_DATA_DIR > the importable reference's own pickles (evopf.py:212-216)
         data_dir = data_dir or os.environ.get("RPO_EVOPF_DATA_DIR")
+        if not data_dir and demand_curve is None and price_curve is None:
+            from .loaders import find_reference_data_dir
+            data_dir = find_reference_data_dir()
+            if not data_dir:
+                import warnings
+                warnings.warn("EVOPFEnv: reference demand/price pickles not found (no `rpo` package importable, no data_dir, "
+                              "no RPO_EVOPF_DATA_DIR): using the synthetic daily curves of rpo_b200.env.loaders", stacklevel=2)
+        self.data_dir = data_dir
         dp = os.path.join(data_dir, "demand.pickle") if data_dir else None
         pp = os.path.join(data_dir, "price.pickle") if data_dir else None
         self.data = DemandLoader(ppc=ppc, rho=0.5, q_rand=True, T=24, min_pf=0.9, max_pf=1.0, regularized=True,

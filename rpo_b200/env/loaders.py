@@ -2,9 +2,10 @@
 (rpo/env/electrical_grid/data/demand.py:7-75, price.py:7-55).
 
 The reference averages two pickled time series into 24-step daily curves.  Those data files are assets of the
-reference and are not redistributed: pass ``curve=`` explicitly, or ``pickle_path=`` pointing at the reference's
-``crawlers/*.pickle`` when the reference is installed beside this package; otherwise a smooth synthetic daily
-profile of the same mean level is used (documented in DESIGN.md).
+reference and are not redistributed: pass ``curve=`` explicitly or ``pickle_path=`` pointing at the reference's
+``crawlers/*.pickle``; EVOPFEnv locates them by itself when the reference package is importable
+(`find_reference_data_dir`); only in stand-alone use (no reference anywhere) a smooth synthetic daily profile of the
+same mean level is used, with a warning (documented in DESIGN.md).
 """
 from __future__ import annotations
 
@@ -13,6 +14,24 @@ import pickle
 import numpy as np
 
 from ..case14 import PD, QD
+
+
+def find_reference_data_dir():
+    """The reference keeps its recorded demand / price series beside its loaders (rpo/env/electrical_grid/data/crawlers,
+    evopf.py:212-216 -> data/demand.py:14, data/price.py:13).  When the reference package `rpo` is importable — which it
+    is whenever rpo_b200 is used as a drop-in under the reference's own algorithm classes — use its files, so that the
+    drop-in EVOPFEnv sees the same exogenous curves.  Returns None when `rpo` cannot be located (stand-alone use)."""
+    import importlib.util
+    import os
+    try:
+        spec = importlib.util.find_spec("rpo")
+    except (ImportError, ValueError):
+        spec = None
+    for root in (list(spec.submodule_search_locations) if spec is not None and spec.submodule_search_locations else []):
+        d = os.path.join(root, "env", "electrical_grid", "data", "crawlers")
+        if os.path.isfile(os.path.join(d, "demand.pickle")) and os.path.isfile(os.path.join(d, "price.pickle")):
+            return d
+    return None
 
 
 def _daily_curve(pickle_path, key, T):

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from .. import ops
-from .spaces import Box
+from .spaces import Box, EnvBase
 
 
 class _CompleteFn(torch.autograd.Function):
@@ -55,7 +55,7 @@ class _ResidFn(torch.autograd.Function):
         return None, ops.pen_resid_bwd(obs, action, g_ineq=g, ineq_mode=1 if ctx.kind == 2 else 0), None
 
 
-class SpringPendulumEnv(object):
+class SpringPendulumEnv(EnvBase):
     metadata = {"render_modes": ["human", "rgb_array"], "render_fps": 30}
 
     def __init__(self, g=10.0, device=None, reference_batch_coupling=False):

@@ -13,18 +13,20 @@ def register_all(force: bool = False) -> bool:
         ("EVOPF-v0", "rpo_b200.env:EVOPFEnv", None),
     ]
     for id_, entry, steps in specs:
+        # gym <= 0.21: `registry` is an EnvRegistry whose specs live in `.env_specs` (it has no __contains__ / __delitem__);
+        # gym >= 0.22 and the test stub: a plain dict
+        specs_map = getattr(registry, "env_specs", None)
+        if specs_map is None:
+            specs_map = registry
         try:
-            present = id_ in registry or id_ in getattr(registry, "env_specs", {})
+            present = id_ in specs_map
         except Exception:
             present = False
         if present and force:
             try:
-                del registry[id_]
+                del specs_map[id_]
             except Exception:
-                try:
-                    del registry.env_specs[id_]
-                except Exception:
-                    pass
+                pass
         if not present or force:
             kw = dict(id=id_, entry_point=entry)
             if steps is not None:
