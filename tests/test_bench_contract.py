@@ -42,11 +42,33 @@ def test_product_arm_line():
     r = d["roofline"]
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-6
     assert d["gpu_launches"] == 2 * 5                                  # one projection + one backward kernel per step
+    assert r["frac"] < 1.0 and r["dense_model"]["frac_dense_model"] > r["frac"]      # `frac` counts executed flops
     e = d["e2e"]
-    assert e["value"] > 0 and e["h2d_bytes_per_step"] == (57 + 14 + 43) * 4 * (1 << 20) and e["d2h_bytes_per_step"] == (43 + 14) * 4 * (1 << 20)
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == (33 + 14 + 43) * 4 * (1 << 20) and e["d2h_bytes_per_step"] == (43 + 14) * 4 * (1 << 20)
+    assert e["full_rows"]["h2d_bytes_per_step"] == (57 + 14 + 43) * 4 * (1 << 20)
     assert e["value"] < d["value"]                                     # host buffers cross PCIe inside the timed region
     c = d["cpu_baseline"]
-    assert c["kind"] == "port" and c["value"] > 0 and c["cores"] >= 1
+    have_ref = os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "rpo", "env", "electrical_grid", "evopf.py"))
+    assert c["kind"] == ("reference" if have_ref else "port") and c["value"] > 0 and c["cores"] >= 1
     o = d["other_configs"]                                             # BASELINE.json configs[0] / configs[1] beside the headline
     assert o["safe_cartpole"]["value"] > 1e9 and o["spring_pendulum"]["value"] > 1e9
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+@pytest.mark.timeout(900)
+def test_reference_arm_train_workload_line():
+    """configs[2] on the host cores: the unmodified reference's RPODDPG.run (needs the reference tree or its oracle/_ref copy)."""
+    if not os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "rpo", "env", "electrical_grid", "evopf.py")):
+        pytest.skip("oracle/_ref not present (run oracle/make_ref_copy.sh)")
+    d = _run("--impl", "reference", "--workload", "train", "--steps", "3", "--warmup", "1")
+    assert d["impl"] == "reference" and d["unit"] == "iterations/s" and d["value"] > 0 and d["steps"] == 3
+    assert d["cpu_baseline"]["kind"] == "reference" and "configs[2]" in d["config"]["workload"]
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+def test_product_arm_train_workload_line():
+    if not os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "rpo", "env", "electrical_grid", "evopf.py")):
+        pytest.skip("oracle/_ref not present (run oracle/make_ref_copy.sh)")
+    d = _run("--workload", "train", "--steps", "40", "--warmup", "5")
+    assert d["unit"] == "iterations/s" and d["value"] > 20 and d["config"]["device"] == "cuda" and d["config"]["replay_size"] >= 40
