@@ -47,7 +47,15 @@ def _rows(t: torch.Tensor, name: str, min_cols: int) -> Tuple[torch.Tensor, int]
     if t.shape[0] <= 1:
         t = t.contiguous()
         return t, t.shape[1]
-    return t, t.stride(0)
+    # The kernels bulk-copy whole row blocks of `ld` floats (TMA): the LAST row must own ld floats inside the allocation
+    # too.  A column-offset view (e.g. s[:, 24:57] of a (B,57) tensor) ends `offset` floats before that: copy it.
+    ld = t.stride(0)
+    if ld != t.shape[1]:
+        end = (t.storage_offset() + t.shape[0] * ld) * t.element_size()
+        if end > t.untyped_storage().nbytes():
+            t = t.contiguous()
+            return t, t.shape[1]
+    return t, ld
 
 
 def _same_batch(B: int, **tensors) -> None:

@@ -17,12 +17,33 @@ from . import ops
 from .case14 import PD, QD, case14
 
 
-class EvopfExoSampler(object):
-    """Draws exogenous rows [pd(14) | qd(14) | price window(24)] on the device with the reference loaders' distributions
-    (data/demand.py:47-67, data/price.py:40-47): case share mixed with Dirichlet(1) over the 11 load buses (rho = .5),
-    total load following a daily curve, qd = pd tan(acos(U(.9,1))) sign(Qd), price = curve (1+N)(1+.1 N)/100."""
+def _daily_curves(demand_curve=None, price_curve=None, T: int = 24):
+    """The 24-step daily curves of the reference loaders (data/demand.py:14-27, data/price.py:13-27): averaged from the
+    reference's recorded series when its package is importable (rpo_b200.env.loaders.find_reference_data_dir), else the
+    synthetic profiles of rpo_b200.env.loaders."""
+    import numpy as np
+    from .env import loaders
+    d = loaders.find_reference_data_dir() if (demand_curve is None or price_curve is None) else None
+    if demand_curve is None:
+        demand_curve = loaders._daily_curve(d + "/demand.pickle", "value", T) if d else loaders.synthetic_curve(T, level=1000.0)
+    if price_curve is None:
+        price_curve = loaders._daily_curve(d + "/price.pickle", "SYS", T) if d else loaders.synthetic_curve(T, level=49.0, swing=0.25)
+    return np.asarray(demand_curve, dtype=np.float64), np.asarray(price_curve, dtype=np.float64)
 
-    def __init__(self, device, seed: int = 0, T: int = 24, default_generator: bool = False):
+
+class EvopfExoSampler(object):
+    """Exogenous rows [pd(14) | qd(14) | price window(24)] drawn on the device with the reference loaders' semantics.
+
+    Demand (data/demand.py:47-67): hour h's total is sum(Pd) * curve[h] / mean(curve); bus shares = case share mixed with a
+    Dirichlet(1) draw over the 11 load buses (rho = .5), qd = pd tan(acos(U(.9,1))) sign(Qd) — independent per hour, so
+    drawing them step by step is the same distribution as the reference's per-episode table.
+    Price (data/price.py:29-55): ONE realisation per episode, price[0:48] = mag_r * [curve | 0] * (1 + N(0,1)^48) / 100 with
+    mag_r = 1 + 0.1 N(0,1) drawn once; the observation at hour h is the window price[h:h+24] of that single realisation,
+    so the look-ahead IS the future price (state[t].price[1] == state[t+1].price[0]).  `new_episode(mask)` redraws the
+    realisation of the replicas whose day restarts."""
+
+    def __init__(self, device, seed: int = 0, T: int = 24, default_generator: bool = False, demand_curve=None,
+                 price_curve=None, n: int = 0):
         """default_generator=True draws from torch's default generator of the device (which CUDA-graph capture
         supports) instead of a private seeded one."""
         self.device = torch.device(device)
@@ -35,15 +56,30 @@ class EvopfExoSampler(object):
         self.load_mask = (pd_case != 0).to(self.device)
         self.q_sign = torch.tensor(bus[:, QD], dtype=torch.float64).sign().to(self.device, torch.float32)
         self.total = float(pd_case.sum() / 100.0)                      # 2.59 pu
-        h = torch.arange(T, dtype=torch.float32)
-        self.demand_curve = (1.0 + 0.16 * torch.sin((h - 9.0) * 2 * math.pi / T)).to(self.device)
-        self.price_curve = (0.49 * (1.0 + 0.25 * torch.sin((h - 15.0) * 2 * math.pi / T))).to(self.device)
+        dc, pc = _daily_curves(demand_curve, price_curve, T)
+        self.demand_curve = torch.tensor(dc / dc.mean(), dtype=torch.float32, device=self.device)   # demand.py:51-52
+        self.price_curve = torch.tensor(pc / 100.0, dtype=torch.float32, device=self.device)        # price / baseMVA, evopf.py:57
+        self.price_ep = torch.zeros(n, 2 * T, device=self.device)      # the current episode's price realisation per replica
+        if n:
+            self.new_episode(None)
 
     def _rand(self, *shape):
         return torch.rand(*shape, generator=self.gen, device=self.device)
 
     def _randn(self, *shape):
         return torch.randn(*shape, generator=self.gen, device=self.device)
+
+    def new_episode(self, mask):
+        """Redraw the episode price realisation (price.py:40-47) of the replicas in `mask` ((N,) bool; None = all).
+        Always draws for all N rows and selects: no data-dependent shapes, so the call can sit inside a CUDA graph."""
+        n = self.price_ep.shape[0]
+        mag = 1.0 + 0.1 * self._randn(n, 1)
+        fresh = torch.zeros_like(self.price_ep)
+        fresh[:, :self.T] = mag * self.price_curve[None] * (1.0 + self._randn(n, self.T))
+        if mask is None:
+            self.price_ep.copy_(fresh)
+        else:
+            self.price_ep.copy_(torch.where(mask[:, None], fresh, self.price_ep))
 
     def rows(self, hour: torch.Tensor) -> torch.Tensor:
         """hour (N,) int64 in [0, T) -> (N, 52) float32."""
@@ -54,25 +90,45 @@ class EvopfExoSampler(object):
         pd = ratio * (self.total * self.demand_curve[hour])[:, None]
         pf = 0.9 + 0.1 * self._rand(n, 14)
         qd = pd * torch.tan(torch.acos(pf)) * self.q_sign[None]
-        idx = (hour[:, None] + self.ar24[None]) % self.T
-        ahead_valid = (hour[:, None] + self.ar24[None]) < self.T
-        price = self.price_curve[idx] * (1 + self._randn(n, 24)) * (1 + 0.1 * self._randn(n, 1)) * ahead_valid
+        if self.price_ep.shape[0] != n:                                # stand-alone use: one fresh realisation per call
+            self.price_ep = torch.zeros(n, 2 * self.T, device=self.device)
+            self.new_episode(None)
+        price = torch.gather(self.price_ep, 1, hour[:, None] + self.ar24[None])     # window [h, h+24) of the realisation
         return torch.cat([pd, qd, price], dim=1).float()
+
+
+class TableExo(object):
+    """Exogenous rows from precomputed per-replica day tables (N, T, 52): e.g. the reference loaders' own draws, so that a
+    batched rollout can be compared with the reference's sequential one on identical data (tests)."""
+
+    def __init__(self, table: torch.Tensor):
+        self.table = table
+        self.device = table.device
+        self.T = table.shape[1]
+        self._ar = torch.arange(table.shape[0], device=table.device)
+
+    def new_episode(self, mask):
+        return None
+
+    def rows(self, hour: torch.Tensor) -> torch.Tensor:
+        return self.table[self._ar, hour]
 
 
 class EvopfVectorEnv(object):
     """N independent EVOPF-v0 replicas on one GPU; `step` = one launch of rpo_evopf_step (evopf.py:348-366 row-wise).
-    Episodes last T = 24 steps (demand.py:69-75) and restart automatically (soc back to 0.2, evopf.py:62-63,243)."""
+    Episodes last T = 24 steps (demand.py:69-75) and restart automatically (soc back to 0.2, evopf.py:62-63,243; a new
+    price realisation, price.py:29-38)."""
 
-    def __init__(self, n: int, device, seed: int = 0, default_generator: bool = False):
+    def __init__(self, n: int, device, seed: int = 0, default_generator: bool = False, exo=None):
         self.n, self.device = n, torch.device(device)
-        self.exo = EvopfExoSampler(self.device, seed, default_generator=default_generator)
+        self.exo = exo if exo is not None else EvopfExoSampler(self.device, seed, default_generator=default_generator, n=n)
         self.T = self.exo.T
         self.hour = torch.zeros(n, dtype=torch.int64, device=self.device)
         self.state = None
 
     def reset(self) -> torch.Tensor:
         self.hour.zero_()
+        self.exo.new_episode(None)
         rows = self.exo.rows(self.hour)
         soc = torch.full((self.n, 5), K.B_LOW + 0.1, device=self.device)
         self.state = torch.cat([rows[:, :28], soc, rows[:, 28:]], dim=1).contiguous()
@@ -84,6 +140,7 @@ class EvopfVectorEnv(object):
         `self.prev_state` and the buffer is overwritten with the next state."""
         nxt_hour = self.hour + 1
         done = nxt_hour >= self.T
+        self.exo.new_episode(done)                                     # replicas whose day is over start a new realisation
         rows = self.exo.rows(torch.where(done, torch.zeros_like(nxt_hour), nxt_hour))
         ns, rew, eqv, iqv = ops.evopf_step(self.state, action, rows)
         # episode restart without a host round trip: soc back to its initial value where the day is over

@@ -89,3 +89,29 @@ def test_batch_size_mismatches_are_rejected_before_the_launch(ops):
         ops.evopf_complete_fwd(torch.zeros(5, 20), z)                  # too few state columns
     with pytest.raises(TypeError):
         ops.evopf_complete_fwd(torch.zeros(5, 57, dtype=torch.float64), z)
+
+
+def test_column_offset_views_are_copied_before_a_bulk_row_copy(ops):
+    """the kernels bulk-copy whole `ld`-float row blocks; a view like s[:, 24:57] of a (B,57) tensor starts 24
+    floats into the allocation, so the block of the last rows would end 24 floats past it.  Such views must reach the
+    kernel as a contiguous copy; views that start at column 0 keep their stride (no copy)."""
+    B = 256
+    st, y = torch.zeros(B, 57), torch.zeros(B, 43)
+    ops.evopf_resid(st[:, :33], y)
+    assert ops.stub.calls[-1][1][0] == st.data_ptr() and ops.stub.calls[-1][1][1] == 57        # prefix view: passed as is
+    wide = torch.zeros(B, 90)
+    ops.evopf_resid(wide[:, 24:57], y)
+    name, args = ops.stub.calls[-1]
+    assert args[1] == 33 and args[0] != wide.data_ptr() + 24 * 4                               # offset view: compact copy
+    ops.evopf_resid(wide[:, 24:90], y)                                                         # same: a row block would overrun
+    assert ops.stub.calls[-1][1][1] == 66
+    ops.evopf_resid(wide[: B - 1, 24:60], y[: B - 1])                                          # a spare row behind it: no copy
+    assert ops.stub.calls[-1][1][1] == 90
+    # the new backward wrappers
+    assert ops.evopf_resid_bwd(st, y, g_ineq=torch.zeros(B, 58), ineq_mode=1).shape == (B, 43)
+    dz, dx = ops.evopf_complete_bwd_penalty(st, y, y, torch.zeros(58), torch.zeros(B))
+    assert dz.shape == (B, 14) and dx.shape == (B, 28)
+    assert ops.cart_resid_bwd(torch.zeros(B, 2), g_eq=torch.zeros(B, 1)).shape == (B, 2)
+    assert ops.pen_resid_bwd(torch.zeros(B, 5), torch.zeros(B, 2), g_ineq=torch.zeros(B, 1), ineq_mode=1).shape == (B, 2)
+    with pytest.raises(ValueError):
+        ops.evopf_resid_bwd(st, y, g_eq=torch.zeros(B - 1, 28))
