@@ -448,7 +448,7 @@ def main():
             graph.replay()
         torch.cuda.synchronize()
     # workload facts for the roofline: mean Newton iterations, steps the reference's loop test would take
-    _, status = ops.evopf_complete_fwd(st, z, return_status=True)
+    _, status = ops.evopf_complete_fwd(st, z, return_status=True, refine=False)      # the fused kernel's own Newton sequence
     n_newton = float((status & 0xff).float().mean())
     not_converged = int(((status >> 8) != 0).sum())      # infeasible power flows exist at ~1e-6 of D1 (reference diverges too)
     fl = out[2].cpu().tolist()

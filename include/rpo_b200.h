@@ -53,6 +53,13 @@ const char* rpo_build_arch(void);
  * tol/max_iters: Newton stop rule (reference: 1e-5 / 50, evopf.py:786).  status: nullable (B) int32. */
 int rpo_evopf_complete_fwd(const float* state, int ld_state, const float* z, float* y, int64_t B, float tol,
                            int max_iters, int32_t* status, void* stream);
+/* rpo_evopf_complete_fwd finishes with a mixed-precision refinement: once every instance of a CTA has ||delta|| < 1e-3 the
+ * last update is a chord step on the float32 LU whose right-hand side is the residual accumulated in float64, which
+ * removes the float32 evaluation noise from the converged point (same stop rule as evopf.py:826-835: the applied update
+ * must have ||delta||_2 < tol).  The _plain variant is the float32 Newton sequence alone — the one rpo_evopf_project
+ * runs before its correction steps; use it where bit-identity with rpo_evopf_project's `y` output is wanted. */
+int rpo_evopf_complete_fwd_plain(const float* state, int ld_state, const float* z, float* y, int64_t B, float tol,
+                                 int max_iters, int32_t* status, void* stream);
 
 /* PFFunctionFn.backward (GRG / implicit-function backward)      rpo/env/electrical_grid/evopf.py:857-910
  * y (B,43) = output of the forward; dl_dy (B,43); dl_dz (B,14) out; dl_dx (B,28) out, nullable.

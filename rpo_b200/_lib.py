@@ -23,6 +23,7 @@ SIGNATURES = {
     "rpo_last_error": (c_char_p, []),
     "rpo_build_arch": (c_char_p, []),
     "rpo_evopf_complete_fwd": (c_int, [_P, c_int, _P, _P, c_int64, c_float, c_int, _P, _P]),
+    "rpo_evopf_complete_fwd_plain": (c_int, [_P, c_int, _P, _P, c_int64, c_float, c_int, _P, _P]),
     "rpo_evopf_complete_bwd": (c_int, [_P, _P, _P, _P, c_int64, _P]),
     "rpo_evopf_direction": (c_int, [_P, c_int, _P, _P, c_int64, _P]),
     "rpo_evopf_correct": (c_int, [_P, c_int, _P, _P, c_int64, c_float, c_float, c_float, c_int, _P, _P]),

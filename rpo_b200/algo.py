@@ -117,7 +117,10 @@ class RPOProjectionMixin(object):
     def process_action(self, state, action_partial, train=True):
         needs_grad = torch.is_grad_enabled() and (action_partial.requires_grad or state.requires_grad)
         if needs_grad or getattr(self, "corr_mode", 0) != 0:
-            action = self.env.complete_partial(state, action_partial)
+            try:                           # EVOPF: the fused kernel's own Newton sequence, so both paths give the same action
+                action = self.env.complete_partial(state, action_partial, refine=False)
+            except TypeError:
+                action = self.env.complete_partial(state, action_partial)
             return self.grad_steps(state, action, train=train)
         # no-grad call sites (rpo_ddpg.py:100,106,233,330): fused completion + correction, one launch
         lr, limit = (self.corr_lr, self.max_steps) if train else (self.eval_lr, self.eval_steps)

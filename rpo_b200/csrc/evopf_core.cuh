@@ -19,27 +19,79 @@ struct RpoVoteSelf {
     RPO_HDM bool operator()(bool p) const { return p; }
 };
 
-// Equality completion = PFFunctionFn.forward (evopf.py:789-855): flat start, Newton on the 22 power-flow
-// equations, closed-form qg / slack pg.  `any` is a vote over the lanes that iterate together (the warp on
-// the GPU; the reference iterates a chunk of 256 together, evopf.py:821-835): everybody keeps iterating
-// until every member has ||delta||_2 < tol, exactly as the reference does inside a chunk.
+// Mixed-precision refinement of the completion.  Once every lane of the voting group has ||delta||_2 < RPO_REFINE_SWITCH the
+// float32 Newton iteration is in its quadratic regime and its sparse LU is good enough to be REUSED: the last update is
+// a chord step  delta = LU^{-1} r(y)  whose right-hand side is the power-flow residual accumulated in float64 (FP64 pipe,
+// otherwise idle).  The stop rule is the reference's (evopf.py:826-835: iterate until the applied update has
+// ||delta||_2 < tol); what changes is how the last update is computed: no Jacobian rebuild / refactorisation, and the
+// float32 evaluation noise of the residual no longer ends up in the converged point (equality residual of the result,
+// evaluated in float64 over 32k D1 instances: max 4.9e-6 / median 1.6e-6 against 8.0e-6 / 1.8e-6 for the float32
+// reference).  The closed-form tail (qg, slack pg; evopf.py:844-848) comes from the same float64 flows.
+// Returns whether every lane of the group has converged; `it` counts applied updates (Newton + chord).
+#ifndef RPO_REFINE_SWITCH
+#define RPO_REFINE_SWITCH RC(1.0e-3)
+#endif
+#ifndef RPO_REFINE_MAX_PASSES
+#define RPO_REFINE_MAX_PASSES 1
+#endif
 template <class Vote>
-RPO_HD int evopf_complete(const real* x, const real* z, real* y, real tol, int max_iters, Vote any) {
-    EvopfPt pt;
-    evopf_init(z, y);
-    int it = 0;
-    bool conv = false;
-    real minpiv = RC(3.0e38);
-    while (true) {
-        real mp;
-        const real n2 = evopf_newton_iter(x, y, pt, &mp);
-        minpiv = FMIN(minpiv, mp);
+RPO_HD bool evopf_refine(const real* x, real* y, const EvopfPt& pt, const real* lu, const real* ipiv, real tol, int max_iters,
+                         int& it, bool& conv, Vote any) {
+    double P[14], Q[14];
+    real r[EVOPF_NN];
+    bool all = false;
+    for (int pass = 0; pass < RPO_REFINE_MAX_PASSES && !all && it < max_iters; ++pass) {   // uniform over the voting group
+        evopf_flows_f64(y, P, Q);
+        evopf_newton_rhs_f64(x, y, P, Q, r);
+        evopf_solve(lu, ipiv, r);
+        const real n2 = evopf_newton_update(r, y);
         ++it;
         conv = sqrt(n2) < tol;
-        if (!any(!conv) || it >= max_iters) break;
+        all = !any(!conv);
     }
-    evopf_eval_flows(y, pt);
-    evopf_tail(x, y, pt);
+    evopf_tail_refined(x, y, pt, P, Q, r);
+    return all;
+}
+
+// Equality completion = PFFunctionFn.forward (evopf.py:789-855): flat start, Newton on the 22 power-flow
+// equations, closed-form qg / slack pg.  `any` is a vote over the lanes that iterate together (the CTA on
+// the GPU; the reference iterates a chunk of 256 together, evopf.py:821-835): everybody keeps iterating
+// until every member has ||delta||_2 < tol, exactly as the reference does inside a chunk.
+// REFINE = true: finish with the mixed-precision refinement above (the stand-alone completion: rpo_evopf_complete_fwd,
+// EVOPFEnv.complete_partial).  REFINE = false: plain float32 Newton, the very sequence the fused projection kernel runs
+// before its correction steps (evopf_project_loop; there the completion point is an intermediate whose equality
+// residual the 10 linearised correction steps raise to ~1e-3 anyway, so the refinement would buy nothing).
+template <bool REFINE, class Vote>
+RPO_HD int evopf_complete(const real* x, const real* z, real* y, real tol, int max_iters, Vote any) {
+    evopf_init(z, y);
+    int it = 0;
+    bool conv = false, tail_ok = false;
+    real minpiv = RC(3.0e38);
+    while (true) {
+        EvopfPt pt;
+        real lu[EVOPF_NLU], ipiv[EVOPF_NN], r[EVOPF_NN];
+        evopf_eval_full(y, pt);
+        minpiv = FMIN(minpiv, evopf_factor(pt, lu, ipiv));
+        evopf_newton_rhs(x, y, pt, r);
+        evopf_solve(lu, ipiv, r);
+        const real dn = sqrt(evopf_newton_update(r, y));
+        ++it;
+        conv = dn < tol;
+        tail_ok = false;
+        bool all;
+        if (REFINE && !any(!(dn < RPO_REFINE_SWITCH)) && it < max_iters) {
+            all = evopf_refine(x, y, pt, lu, ipiv, tol, max_iters, it, conv, any);
+            tail_ok = true;
+        } else {
+            all = !any(!conv);
+        }
+        if (all || it >= max_iters) break;
+    }
+    if (!tail_ok) {                                    // no refinement pass ran last (max_iters hit / tol above the switch)
+        EvopfPt pt;
+        evopf_eval_flows(y, pt);
+        evopf_tail(x, y, pt);
+    }
     int st = it & RPO_ST_ITERS_MASK;
     if (!conv) st |= RPO_ST_NOT_CONVERGED;
     if (!(minpiv >= RPO_PIVOT_FLOOR)) st |= RPO_ST_SMALL_PIVOT;

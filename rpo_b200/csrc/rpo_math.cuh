@@ -84,6 +84,32 @@ RPO_HD void rpo_sincosf_small(float x, float* sp, float* cp) {
     *cp = fmaf(pc, x2, 1.0f);
 }
 
+// ---- sincos for the mixed-precision refinement of the completion ----------------------------------------
+// sin x = x + x^3 ps(x^2), cos x = 1 + x^2 pc(x^2): the leading terms are exact, so evaluating the small corrections
+// ps / pc in float32 (the polynomials of rpo_sincosf_small) and only the final combination in float64 gives an absolute
+// error of 6e-9 for |x| <= 0.6 and 2e-8 for |x| <= 1 (pure float32: 4e-8 / 5e-8 plus the rounding of the result) at the
+// price of 4 FP64 instructions.  Larger angles (never met in power-flow states) fall back to the float32 values.
+RPO_HD void rpo_sincos_mixed(float x, double* sp, double* cp) {
+    if (fabsf(x) <= 1.6f) {
+        const float x2 = x * x;
+        float ps = fmaf(x2, 0x1.60ff98p-19f, -0x1.9fae94p-13f);
+        ps = fmaf(ps, x2, 0x1.111036p-7f);
+        ps = fmaf(ps, x2, -0x1.555554p-3f);
+        float pc = fmaf(x2, -0x1.19d6b8p-22f, 0x1.9f9cb4p-16f);
+        pc = fmaf(pc, x2, -0x1.6c14f8p-10f);
+        pc = fmaf(pc, x2, 0x1.55555p-5f);
+        pc = fmaf(pc, x2, -0.5f);
+        const double xd = (double)x, x2d = xd * xd;
+        *sp = fma(xd * x2d, (double)ps, xd);
+        *cp = fma(x2d, (double)pc, 1.0);
+    } else {
+        float s_, c_;
+        rpo_sincosf(x, &s_, &c_);
+        *sp = (double)s_;
+        *cp = (double)c_;
+    }
+}
+
 #if defined(__CUDA_ARCH__)
 // device, float only (the CUDA build is always float)
 RPO_D float rpo_rcp_approx(float x) {
@@ -94,6 +120,7 @@ RPO_D float rpo_rcp_approx(float x) {
 #define FMA(a, b, c) __fmaf_rn((a), (b), (c))
 #define SINCOS(x, s, c) rpo_sincosf((x), (s), (c))
 #define SINCOS_SMALL(x, s, c) rpo_sincosf_small((x), (s), (c))
+#define SINCOS_REFINE(x, s, c) rpo_sincos_mixed((x), (s), (c))
 #define RCP(x) rpo_rcp_approx(x)
 #define FMIN(a, b) fminf((a), (b))
 #define FMAX(a, b) fmaxf((a), (b))
@@ -105,6 +132,9 @@ static inline void rpo_sincos_(float x, float* s, float* c) { rpo_sincosf(x, s, 
 static inline void rpo_sincos_(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
 static inline void rpo_sincos_small_(float x, float* s, float* c) { rpo_sincosf_small(x, s, c); }
 static inline void rpo_sincos_small_(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
+static inline void rpo_sincos_refine_(float x, double* s, double* c) { rpo_sincos_mixed(x, s, c); }
+static inline void rpo_sincos_refine_(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }   // float64 validation build
+#define SINCOS_REFINE(x, s, c) rpo_sincos_refine_((x), (s), (c))
 #define FMA(a, b, c) rpo_fma_((real)(a), (real)(b), (real)(c))
 #define SINCOS(x, s, c) rpo_sincos_((x), (s), (c))
 #define SINCOS_SMALL(x, s, c) rpo_sincos_small_((x), (s), (c))

@@ -23,8 +23,8 @@ class _CompleteFn(torch.autograd.Function):
     where the reference saves a (B,28,43) Jacobian and a (B,22,22) inverse (evopf.py:851-853)."""
 
     @staticmethod
-    def forward(ctx, x, z, tol, max_iters):
-        y = ops.evopf_complete_fwd(x, z, tol=tol, max_iters=max_iters)
+    def forward(ctx, x, z, tol, max_iters, refine=True):
+        y = ops.evopf_complete_fwd(x, z, tol=tol, max_iters=max_iters, refine=refine)
         ctx.save_for_backward(y)
         return y
 
@@ -32,7 +32,7 @@ class _CompleteFn(torch.autograd.Function):
     def backward(ctx, dl_dy):
         (y,) = ctx.saved_tensors
         dz, dx = ops.evopf_complete_bwd(y, dl_dy.contiguous(), need_dx=ctx.needs_input_grad[0])
-        return dx, dz, None, None
+        return dx, dz, None, None, None
 
 
 class _ResidFn(torch.autograd.Function):
@@ -199,10 +199,13 @@ class EVOPFEnv(EnvBase):
                 action[:, -self.ne - self.nbus:-self.ne], action[:, -self.ne:])
 
     # ---- hard-constraint protocol -----------------------------------------------------------------------
-    def complete_partial(self, state, action_partial):          # evopf.py:724-727
+    def complete_partial(self, state, action_partial, refine=True):          # evopf.py:724-727
+        """refine=True (default): float32 Newton finished by a float64-residual chord step (equality residual below the
+        float32 reference's); refine=False: the plain float32 Newton sequence of the fused projection kernel, which
+        rpo_b200.algo.process_action uses so that its autograd path and its fused no-grad path give identical actions."""
         if action_partial.dim() == 1:
             action_partial = action_partial.view(1, -1)
-        return _CompleteFn.apply(state[:, :self.xdim], action_partial, self.newton_tol, self.newton_max_iters)
+        return _CompleteFn.apply(state[:, :self.xdim], action_partial, self.newton_tol, self.newton_max_iters, refine)
 
     def eq_resid(self, state, action):                          # evopf.py:520-546 (differentiable, like the reference's)
         return _ResidFn.apply(state, action, 0)

@@ -70,7 +70,9 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 # ------------------------------------------------------------------------------------------- EVOPF
-def evopf_complete_fwd(state, z, tol: float = 1e-5, max_iters: int = 50, return_status: bool = False):
+def evopf_complete_fwd(state, z, tol: float = 1e-5, max_iters: int = 50, return_status: bool = False, refine: bool = True):
+    """refine=True: rpo_evopf_complete_fwd (float32 Newton + float64-residual chord step); refine=False: the plain float32
+    Newton sequence of the fused projection kernel (rpo_evopf_complete_fwd_plain), bit-identical to evopf_project's y."""
     lib = _lib.load()
     state, ld = _rows(state, "state", 28)
     z = _dev(z, "z", 14)
@@ -79,8 +81,9 @@ def evopf_complete_fwd(state, z, tol: float = 1e-5, max_iters: int = 50, return_
     y = torch.empty(B, 43, dtype=torch.float32, device=z.device)
     status = torch.empty(B, dtype=torch.int32, device=z.device) if return_status else None
     with torch.cuda.device(z.device):
-        _lib.check(lib.rpo_evopf_complete_fwd(state.data_ptr(), ld, z.data_ptr(), y.data_ptr(), B, tol, max_iters,
-                                              _ptr(status), _stream(z)), "rpo_evopf_complete_fwd")
+        fn = lib.rpo_evopf_complete_fwd if refine else lib.rpo_evopf_complete_fwd_plain
+        _lib.check(fn(state.data_ptr(), ld, z.data_ptr(), y.data_ptr(), B, tol, max_iters, _ptr(status), _stream(z)),
+                   "rpo_evopf_complete_fwd")
     return (y, status) if return_status else y
 
 

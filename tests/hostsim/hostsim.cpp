@@ -8,9 +8,10 @@
 
 extern "C" {
 
-void hs_evopf_complete(const real* state, int ld, const real* z, real* y, int B, real tol, int max_iters, int* status) {
+void hs_evopf_complete(const real* state, int ld, const real* z, real* y, int B, real tol, int max_iters, int* status, int refine) {
     for (int b = 0; b < B; ++b) {
-        int st = evopf_complete(state + (long)b * ld, z + (long)b * 14, y + (long)b * 43, tol, max_iters, RpoVoteSelf());
+        int st = refine ? evopf_complete<true>(state + (long)b * ld, z + (long)b * 14, y + (long)b * 43, tol, max_iters, RpoVoteSelf())
+                        : evopf_complete<false>(state + (long)b * ld, z + (long)b * 14, y + (long)b * 43, tol, max_iters, RpoVoteSelf());
         if (status) status[b] = st;
     }
 }

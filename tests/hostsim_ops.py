@@ -42,12 +42,12 @@ def _t(a):
 f = ctypes.c_float
 
 
-def evopf_complete_fwd(state, z, tol=1e-5, max_iters=50, return_status=False):
+def evopf_complete_fwd(state, z, tol=1e-5, max_iters=50, return_status=False, refine=True):
     s, zz = _np(state), _np(z, 14)
     B = zz.shape[0]
     y = np.zeros((B, 43), np.float32)
     st = np.zeros(B, np.int32)
-    lib().hs_evopf_complete(_P(s), s.shape[1], _P(zz), _P(y), B, f(tol), max_iters, _P(st))
+    lib().hs_evopf_complete(_P(s), s.shape[1], _P(zz), _P(y), B, f(tol), max_iters, _P(st), int(bool(refine)))
     return (_t(y), _t(st)) if return_status else _t(y)
 
 
@@ -80,7 +80,7 @@ def evopf_project(state, z, lr, momentum, corr_eps, n_steps, tol=1e-5, max_iters
     s, zz = _np(state), _np(z, 14)
     B = zz.shape[0]
     if n_steps == 0:
-        y = evopf_complete_fwd(state, z, tol, max_iters)
+        y = evopf_complete_fwd(state, z, tol, max_iters, refine=False)
         return y.clone(), (y if want_y else None), (_t(np.zeros(1, np.int32)) if want_flags else None), None
     y, yc = np.zeros((B, 43), np.float32), np.zeros((B, 43), np.float32)
     flags, st = np.zeros(max(n_steps, 1), np.int32), np.zeros(B, np.int32)

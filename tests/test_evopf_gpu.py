@@ -29,12 +29,18 @@ def test_complete_fwd_bwd(B, dist, evopf_oracle, evopf_oracle64):
     assert rel_err(y, y_o).max() <= Y_RTOL
     assert (status >> 8).max() == 0, "non-converged / small-pivot flags set"
     assert (status & 0xff).max() <= 8
-    # equality residual of OUR y, evaluated by the oracle in float64 (removes the checker's own f32 noise)
+    # equality residual of OUR y (mixed-precision refined completion), evaluated in float64 (removes the checker's own
+    # float32 noise): at or below the Newton tolerance on every row, and not above the float32 reference's on the same rows
     r = evopf_oracle64.eq_resid(st.double(), y.double()).abs().max(dim=1).values
     r_ref = evopf_oracle64.eq_resid(st.double(), y_o.double()).abs().max(dim=1).values
-    assert r.max() <= 1.5 * EQ_TOL
-    assert (r > EQ_TOL).double().mean() <= 1e-3
-    assert r.max() <= 2.0 * r_ref.max() + 2e-6
+    assert r.max() <= EQ_TOL
+    assert r.max() <= r_ref.max() + (2e-6 if B < 256 else 0.0)            # tiny batches: a maximum over a handful of rows
+    if B >= 256:
+        assert r.median() <= r_ref.median() and (r > EQ_TOL).double().mean() <= (r_ref > EQ_TOL).double().mean()
+    # the plain float32 sequence (what the fused projection kernel runs before its correction steps): same noise class
+    y_plain = ops.evopf_complete_fwd(st.cuda(), z.cuda(), refine=False).cpu()
+    r_plain = evopf_oracle64.eq_resid(st.double(), y_plain.double()).abs().max(dim=1).values
+    assert r_plain.max() <= 1.5 * EQ_TOL and rel_err(y_plain, y_o).max() <= Y_RTOL
     # GRG backward
     g = synth.upstream_grad(B, 43)
     dz, dx = ops.evopf_complete_bwd(y.cuda(), g.cuda())
@@ -72,7 +78,7 @@ def test_direction_correct_project(B, dist, evopf_oracle):
     assert (rel_err(ycm.cpu(), ycm_o) > Y_RTOL).double().mean() <= OUTLIER_FRAC
     # fused projection == complete followed by correct (same kernels' math, bit-for-bit)
     yp, y1, fl2, status = ops.evopf_project(st.cuda(), z.cuda(), 1e-4, 0.0, 1e-5, 10, want_y=True, want_status=True)
-    y_sep = ops.evopf_complete_fwd(st.cuda(), z.cuda())
+    y_sep = ops.evopf_complete_fwd(st.cuda(), z.cuda(), refine=False)      # the fused kernel's own (plain float32) Newton sequence
     yc_sep, _ = ops.evopf_correct(st.cuda(), y_sep, 1e-4, 0.0, 1e-5, 10)
     assert torch.equal(y1, y_sep)
     assert torch.equal(yp, yc_sep)
@@ -182,3 +188,18 @@ def test_step_and_resid_optional_outputs():
         ns2, rew2, e2, i2 = ops.evopf_step(st_d, y, exo, want_viol=False)
         assert e2 is None and i2 is None and torch.equal(ns, ns2) and torch.equal(rew, rew2)
         assert torch.equal(eqv, eq) and torch.equal(iqv, torch.clamp(iq, 0))
+
+
+def test_small_pivot_flag_fires_on_a_collapsed_voltage_profile():
+    """RPO_STATUS_SMALL_PIVOT (reference: torch.inverse would raise / return garbage on a singular Jacobian, evopf.py:831):
+    generator voltages of 1e-9 pu make the flow-Jacobian rows of those buses O(V), so their static-order pivots fall below 1e-6."""
+    from rpo_b200 import ops, synth
+    st = synth.evopf_states(64, seed=70)
+    z = synth.evopf_partial_actions(st, seed=71)
+    z[::2, 4:9] = 1e-9                                          # vm_spv of every second instance
+    y, status = ops.evopf_complete_fwd(st.cuda(), z.cuda(), return_status=True)
+    status = status.cpu().numpy()
+    assert ((status[::2] & 0x200) != 0).all(), status[:8]
+    assert ((status[1::2] >> 8) == 0).all()                      # the untouched instances are unaffected (no cross-instance coupling)
+    _, status_p = ops.evopf_complete_fwd(st.cuda(), z.cuda(), return_status=True, refine=False)
+    assert ((status_p.cpu().numpy()[::2] & 0x200) != 0).all()

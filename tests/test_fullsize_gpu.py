@@ -47,6 +47,36 @@ def test_convergence_and_residual_at_full_size(data, evopf_oracle64):
     assert data["flags"].cpu().tolist() == [1] * K                      # the reference would take all 10 steps
 
 
+def test_refined_completion_residual_not_above_reference_at_full_size(data, evopf_oracle, evopf_oracle64):
+    """north_star: "equality residual at or below the reference's Newton tolerance".  The stand-alone completion
+    (rpo_evopf_complete_fwd: float32 Newton + float64-residual chord step) over all 2^20 instances; its equality residual,
+    evaluated in float64, against the float32 reference's on the same 65,536 rows: maximum, median, and fraction above 1e-5."""
+    from oracle.rpo_oracle import EvopfOracle
+    from rpo_b200 import ops
+    y, status = ops.evopf_complete_fwd(data["st_d"], data["z_d"], return_status=True)
+    ok = ((status >> 8) == 0)
+    assert int((~ok).sum()) <= 8
+    # every row, by our own float32 residual kernel (its evaluation noise is ~2e-6 on top of the true residual)
+    eq, _ = ops.evopf_resid(data["st_d"], y, want_ineq=False)
+    r32 = eq.abs().max(dim=1).values[ok]
+    assert float(r32.max()) <= 1.2 * EQ_TOL and float((r32 > EQ_TOL).float().mean()) <= 1e-5
+    idx = torch.arange(0, B, 16)
+    idx = idx[ok.cpu()[idx]]
+    st, z = data["st"][idx], data["z"][idx]
+    y_ref = evopf_oracle.complete_partial_fwd(st, z)
+    chk32 = EvopfOracle(dtype=torch.float64, const_dtype=torch.float32)     # the reference's own (float32) network constants
+    for chk in (chk32, evopf_oracle64):
+        r = chk.eq_resid(st.double(), y.cpu()[idx].double()).abs().max(dim=1).values
+        r_ref = chk.eq_resid(st.double(), y_ref.double()).abs().max(dim=1).values
+        assert float(r.max()) <= float(r_ref.max()) and float(r.max()) <= EQ_TOL
+        assert float(r.median()) <= float(r_ref.median())
+        assert float((r > EQ_TOL).double().mean()) <= float((r_ref > EQ_TOL).double().mean())
+        assert float(torch.quantile(r, 0.999)) <= float(torch.quantile(r_ref, 0.999))
+    assert rel_err(y.cpu()[idx], y_ref).max() <= Y_RTOL
+    # refined and plain completions agree to the float32 noise of the plain one
+    assert rel_err(y.cpu()[idx], data["y"].cpu()[idx]).max() <= 2e-5
+
+
 def test_oracle_parity_on_subsample(data, evopf_oracle):
     from oracle.rpo_oracle import grad_steps_margins
     orc = evopf_oracle
@@ -86,7 +116,7 @@ def test_shard_equivalence_and_permutation(data):
 
 def test_fused_equals_separate_and_backward_linearity(data):
     from rpo_b200 import ops
-    y_sep = ops.evopf_complete_fwd(data["st_d"], data["z_d"])
+    y_sep = ops.evopf_complete_fwd(data["st_d"], data["z_d"], refine=False)
     assert torch.equal(y_sep, data["y"])
     yc_sep, _ = ops.evopf_correct(data["st_d"], y_sep, LR, MOM, EPS, K, want_flags=False)
     assert torch.equal(yc_sep, data["yc"])

@@ -29,11 +29,11 @@ def _P(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def _complete(lib, st, z, npd, creal, tol=1e-5):
+def _complete(lib, st, z, npd, creal, tol=1e-5, refine=1):
     B = st.shape[0]
     y = np.zeros((B, 43), npd)
     status = np.zeros(B, np.int32)
-    lib.hs_evopf_complete(_P(st), st.shape[1], _P(z), _P(y), B, creal(tol), 50, _P(status))
+    lib.hs_evopf_complete(_P(st), st.shape[1], _P(z), _P(y), B, creal(tol), 50, _P(status), refine)
     return y, status
 
 
@@ -143,7 +143,7 @@ def test_fused_single_loop_equals_complete_then_correct(libs):
     B = 500
     st = synth.evopf_states(B, seed=21).numpy().copy()
     z = synth.evopf_partial_actions(torch.tensor(st), seed=22).numpy().copy()
-    y, status = _complete(lib, st, z, np.float32, ctypes.c_float)
+    y, status = _complete(lib, st, z, np.float32, ctypes.c_float, refine=0)     # the plain Newton sequence the fused loop runs
     yc = y.copy()
     flags = np.zeros(10, np.int32)
     lib.hs_evopf_correct(_P(st), 57, _P(yc), B, ctypes.c_float(1e-4), ctypes.c_float(0.5), ctypes.c_float(1e-5), 7, _P(flags))
@@ -190,3 +190,33 @@ def test_long_correction_and_momentum(K, mom, lr, evopf_oracle):
     assert k == K and flags.tolist() == [1] * K
     rel = (yc_h - yc_o).abs().max(dim=1).values / yc_o.abs().max(dim=1).values
     assert float(rel.median()) <= 1e-6 and int((rel > Y_RTOL).sum()) <= 1
+
+
+@pytest.mark.parametrize("dist", ["D1", "D2"])
+def test_refined_completion_residual_is_below_the_float32_reference(libs, dist, evopf_oracle):
+    """The mixed-precision refinement (float32 Newton + one chord step on the float64-accumulated residual): same stop rule,
+    y within tolerance of the reference, and an equality residual (evaluated in float64 on the reference's float32
+    constants) BELOW the float32 reference's on the same rows — in the median, the upper quantiles and the maximum."""
+    from oracle.rpo_oracle import EvopfOracle
+    from rpo_b200 import synth
+    lib = libs["f32"]
+    B = 8192
+    st = synth.evopf_states(B, seed=31)
+    z = synth.evopf_partial_actions(st, seed=32, dist=dist)
+    y_ref = evopf_oracle.complete_partial_fwd(st, z)
+    s_np, z_np = st.numpy().copy(), z.numpy().copy()
+    y_r, status_r = _complete(lib, s_np, z_np, np.float32, ctypes.c_float, refine=1)
+    y_p, status_p = _complete(lib, s_np, z_np, np.float32, ctypes.c_float, refine=0)
+    assert (status_r >> 8).max() == 0 and (status_p >> 8).max() == 0
+    chk = EvopfOracle(dtype=torch.float64, const_dtype=torch.float32)
+    res = lambda y: chk.eq_resid(st.double(), torch.as_tensor(y).double()).abs().max(dim=1).values
+    r_ref, r_r, r_p = res(y_ref), res(y_r), res(y_p)
+    q = torch.tensor([0.5, 0.99, 0.999], dtype=torch.float64)
+    for a, b in zip(torch.quantile(r_r, q), torch.quantile(r_ref, q)):
+        assert float(a) <= 0.85 * float(b), (float(a), float(b))
+    assert float(r_r.max()) <= 0.8 * float(r_ref.max()) and float(r_r.max()) <= 0.6e-5
+    assert float((r_r > 1e-5).double().mean()) <= float((r_ref > 1e-5).double().mean())
+    assert float(r_p.max()) <= 1.3 * float(r_ref.max())                       # the plain sequence: same noise class as the reference
+    assert rel_err(torch.as_tensor(y_r), y_ref).max() <= 2e-5
+    # the refinement replaces Newton iterations, it does not add to them: applied updates per instance (self vote)
+    assert (status_r & 0xff).mean() <= (status_p & 0xff).mean() + 0.5

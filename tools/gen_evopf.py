@@ -383,6 +383,80 @@ class Gen(object):
         e("}")
         e("")
 
+    def gen_refine(self):
+        """float64 flows for the mixed-precision refinement of the completion: the float32 sparse LU of the
+        last Newton iteration is reused for a chord step whose right-hand side is the residual with the flows accumulated
+        in float64 (the FP64 pipe is otherwise idle), which removes the float32 evaluation noise from the converged point;
+        the closed-form tail (qg, slack pg) is taken from the same float64 flows plus the first-order effect of the step."""
+        e = self.emit
+
+        def dlit(x):
+            return "%.17g" % float(np.float32(x))
+
+        e("// Bus power flows accumulated in float64 (network constants = the float32-rounded Y-bus the reference holds,")
+        e("// evopf.py:260-266); sincos by rpo_sincos_mixed (SINCOS_REFINE).")
+        e("RPO_HD void evopf_flows_f64(const real* y, double* P, double* Q) {")
+        e("    double vr[14], vi[14];")
+        for i in range(self.nb):
+            e("    { double s_, c_; SINCOS_REFINE(y[%d], &s_, &c_); vr[%d] = (double)y[%d] * c_; vi[%d] = (double)y[%d] * s_; }"
+              % (K.VA0 + i, i, K.VM0 + i, i, K.VM0 + i))
+        for i in range(self.nb):
+            ta, tb = [], []
+            for j in self.nz[i]:
+                g, b = self.G[i, j], self.B[i, j]
+                if g != 0:
+                    ta.append((dlit(g), "vr[%d]" % j))
+                    tb.append((dlit(g), "vi[%d]" % j))
+                ta.append((dlit(-b), "vi[%d]" % j))
+                tb.append((dlit(b), "vr[%d]" % j))
+            e("    {")
+            e("    double a_ = %s * %s, b_ = %s * %s;" % (ta[0][0], ta[0][1], tb[0][0], tb[0][1]))
+            for c, v in ta[1:]:
+                e("    a_ = fma(%s, %s, a_);" % (c, v))
+            for c, v in tb[1:]:
+                e("    b_ = fma(%s, %s, b_);" % (c, v))
+            # every bus needs P except none; Q is needed at the PQ buses (Newton rows) and the generator buses (tail)
+            e("    P[%d] = fma(vr[%d], a_, vi[%d] * b_);" % (i, i, i))
+            e("    Q[%d] = fma(vi[%d], a_, -(vr[%d] * b_));" % (i, i, i))
+            e("    }")
+        e("}")
+        e("")
+        e("// Newton right-hand side from float64 flows (rounded to `real` once, at the end).")
+        e("RPO_HD void evopf_newton_rhs_f64(const real* x, const real* y, const double* P, const double* Q, real* r) {")
+        for k, (kind, i) in enumerate(self.eqs):
+            if kind == "P":
+                if i in self.pv:
+                    g = self.spv.index(i)
+                    e("    r[%d] = (real)((((double)y[%d] + (double)y[%d]) - (double)x[%d]) - P[%d]);" % (k, K.PG0 + g, K.PE0 + g, i, i))
+                else:
+                    e("    r[%d] = (real)((-(double)x[%d]) - P[%d]);" % (k, i, i))
+            else:
+                e("    r[%d] = (real)((-(double)x[%d]) - Q[%d]);" % (k, 14 + i, i))
+        e("}")
+        e("")
+        e("// Step 2 of the completion (evopf.py:844-848) after a refinement step: P, Q are the float64 flows at the point the")
+        e("// step started from, r the scaled step just applied (theta += r, V += V r), pt the Jacobian terms of the last Newton")
+        e("// point: flow(y_new) = flow(y_old) + F[L, w] r up to |dF| |r| <= ~40 * RPO_REFINE_SWITCH * tol (4e-7 at 1e-3 / 1e-5).")
+        e("RPO_HD void evopf_tail_refined(const real* x, real* y, const EvopfPt& pt, const double* P, const double* Q, const real* r) {")
+        Lrows = self.L_rows()
+        for li, row in enumerate(Lrows):
+            terms = []
+            for c, unk in enumerate(self.unk):
+                f = self.F(row, unk)
+                if f is not None:
+                    terms.append((f, "r[%d]" % c))
+            e("    {")
+            e("    real u_;")
+            self.accum("u_", terms)
+            if row[0] == "P":
+                e("    y[%d] = (real)((((double)x[%d] - (double)y[%d]) + P[%d]) + (double)u_);" % (K.PG0 + 0, self.slack, K.PE0 + 0, self.slack))
+            else:
+                g = self.spv.index(row[1])
+                e("    y[%d] = (real)(((double)x[%d] + Q[%d]) + (double)u_);" % (K.QG0 + g, 14 + row[1], row[1]))
+            e("    }")
+        e("}")
+        e("")
+
     def gen_resid(self):
         e = self.emit
         e("// eq_resid (evopf.py:520-546) from a flows-evaluated point; returns max |resid|, optionally stores the 28 values.")
@@ -698,6 +772,7 @@ class Gen(object):
         self.gen_eval()
         self.gen_factor()
         self.gen_newton()
+        self.gen_refine()
         self.gen_resid()
         self.gen_backward()
         self.gen_vjp()
@@ -724,7 +799,13 @@ def op_stats(txt):
     post = fl("evopf_direction_pre", "evopf_direction_fin", "evopf_rhs_t", "evopf_solve_t", "evopf_colsums", "evopf_solve")
     corr = fl("evopf_eval_full", "evopf_eq_resid", "evopf_ineq", "evopf_factor") + post + 2 * 43
     bwd = fl("evopf_eval_full", "evopf_factor", "evopf_rhs_t", "evopf_solve_t", "evopf_colsums", "evopf_backward")
+    fb = txt[txt.index("RPO_HD void evopf_flows_f64"):]
+    fb = fb[:fb.index("\n}\n")]
+    dp_fma = fb.count("fma(") + 14 * 2                                 # rpo_sincos_mixed: 2 fma + 2 mul in float64 per bus
+    dp_mul = len(re.findall(r"[\w\]\)] \* [\w\(-]", fb)) + 14 * 2
+    per["evopf_flows_f64"] = dict(fma=dp_fma, mul=dp_mul, add=0, flop=2 * dp_fma + dp_mul, precision="float64")
     return dict(per_function=per, newton_iter_flop=newton, corr_step_flop=corr, tail_flop=fl("evopf_tail"),
+                refine_pass_f32_flop=fl("evopf_solve", "evopf_newton_update", "evopf_tail_refined") + 22 + 14 * 17, refine_pass_f64_flop=2 * dp_fma + dp_mul,
                 backward_flop=bwd, note="general-path sincos not counted (small-angle path taken by the data)")
 
 

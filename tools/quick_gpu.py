@@ -17,7 +17,7 @@ def timeit(f, n=10, reps=5):
         ts.append(e0.elapsed_time(e1)/n)
     ts.sort()
     return ts[len(ts)//2]
-y, status = ops.evopf_complete_fwd(st, z, return_status=True)
+y, status = ops.evopf_complete_fwd(st, z, return_status=True, refine=False)
 print('iters mean', float((status & 0xff).float().mean()), 'flagged', int(((status>>8)!=0).sum()))
 t_f = timeit(lambda: ops.evopf_complete_fwd(st, z))
 t_c = timeit(lambda: ops.evopf_correct(st, y, 1e-4, 0.0, 1e-5, 10))

@@ -21,7 +21,7 @@ for dist in ('D1', 'D2'):
     for lb in range(14, 23):
         B = 1 << lb
         st = synth.evopf_states(B, seed=7).cuda(); z = synth.evopf_partial_actions(st, seed=8, dist=dist).cuda(); g = synth.upstream_grad(B, 43).cuda()
-        _, status = ops.evopf_complete_fwd(st, z, return_status=True)
+        _, status = ops.evopf_complete_fwd(st, z, return_status=True, refine=False)
         def step():
             yc, y, fl, _ = ops.evopf_project(st, z, 1e-4, 0.0, 1e-5, 10, want_y=True)
             ops.evopf_complete_bwd(y, g, need_dx=False)
