@@ -29,7 +29,7 @@ import torch.distributed as dist  # noqa: E402
 import torch.nn as nn  # noqa: E402
 import torch.nn.functional as F  # noqa: E402
 
-from rpo_b200.algo import RPOProjectionMixin, complete_partial_with_penalty  # noqa: E402
+from rpo_b200.algo import RPOProjectionMixin, complete_partial_squashed, process_action_squashed  # noqa: E402
 from rpo_b200.box import BoxConstraint  # noqa: E402
 from rpo_b200.dist import FlatGradBucket, broadcast_parameters  # noqa: E402
 from rpo_b200.env import EVOPFEnv  # noqa: E402
@@ -92,24 +92,30 @@ def main():
     opt_al = torch.optim.Adam([log_alpha], lr=3e-4, capturable=a.graph)
     replay = DeviceReplay(a.envs * 64, dev, default_generator=a.graph, state=57, action=43, next_state=57, reward=1, done=1)
 
-    def policy(net, s, noise=0.0):
-        """box(tanh(net(s)), s) with the state-dependent battery bounds: ONE launch of rpo_box_fwd (f-1; policy.py:30-31)."""
+    def pre_box(net, s, noise=0.0):
+        """The policy output BEFORE the action box, and whether the box still has to apply the tanh: the box itself is
+        fused into the projection / completion kernels (rpo_evopf_project_squashed, SURVEY f-1; policy.py:30-31)."""
         if sac:
-            return sample(net, s)[0]
+            return sample(net, s)[0], False
         if not noise:
-            return box.squash(net(s), s)
+            return net(s), True
         u = torch.tanh(net(s))
-        return box((u + noise * torch.randn_like(u)).clamp(-1, 1), s)
+        return (u + noise * torch.randn_like(u)).clamp(-1, 1), False
 
     def sample(net, s):
-        """tanh-Gaussian policy (policy.py:48-64): returns (partial action in the box, log_pi (B,1))."""
+        """tanh-Gaussian policy (policy.py:48-64): returns (tanh sample in [-1, 1] — the box is fused downstream —, log_pi (B,1))."""
         mean, log_std = net(s).split(14, dim=1)
         log_std = (log_std - 3).clamp(-20, 2)
         u = mean + log_std.exp() * torch.randn_like(mean)
         y = torch.tanh(u)
         logp = -0.5 * ((u - mean) / log_std.exp()) ** 2 - log_std - 0.9189385332046727
         logp = logp - torch.log(box.action_scale(s) * (1 - y.pow(2)) + 1e-6)
-        return box(y, s), logp.sum(1, keepdim=True)
+        return y, logp.sum(1, keepdim=True)
+
+    def project(net, s, noise=0.0):
+        """box + completion + correction of the policy output in ONE launch (no-grad call sites, rpo_ddpg.py:96-106,327-332)."""
+        u, need_tanh = pre_box(net, s, noise)
+        return process_action_squashed(proj, box, s, u, train=True, tanh=need_tanh)
 
     venv.reset()
     last_rew = torch.zeros(a.envs, device=dev)
@@ -120,7 +126,7 @@ def main():
         """Rollout step of all replicas + critic forward/backward; ends where the critic all-reduce goes."""
         with torch.no_grad():                           # rollout of all replicas (rpo_ddpg.py:96-118, vectorised)
             state = venv.state
-            act = proj.process_action(state, policy(actor, state, noise=0.1))
+            act = project(actor, state, noise=0.1)
             nxt, rew, done, _, _ = venv.step(act, inplace=True)
             replay.extend(state=venv.prev_state, action=act, next_state=nxt, reward=rew, done=done.float())
             last_rew.copy_(rew)
@@ -129,10 +135,10 @@ def main():
         with torch.no_grad():                           # critic target (rpo_ddpg.py:327-332 / rpo_sac.py:340-347)
             if sac:
                 nz, nlogp = sample(actor, smp["next_state"])
-                na = proj.process_action(smp["next_state"], nz)
+                na = process_action_squashed(proj, box, smp["next_state"], nz, train=True, tanh=False)
                 nq = critic_t(torch.cat([smp["next_state"], na], 1)).min(dim=1, keepdim=True).values - log_alpha.exp() * nlogp
             else:
-                na = proj.process_action(smp["next_state"], policy(actor_t, smp["next_state"]))
+                na = project(actor_t, smp["next_state"])
                 nq = critic_t(torch.cat([smp["next_state"], na], 1))
             tq = smp["reward"] + 0.95 * (1 - smp["done"]) * nq
         b_critic.zero_()
@@ -154,14 +160,15 @@ def main():
             s = hold["state"]
             if sac:                                     # rpo_sac.py:322-338
                 zs, logp = sample(actor, s)
-                # autograd: ONE backward kernel for the GRG solve and the nju . ineq_dist penalty (rpo_sac.py:324-334)
-                act_c, pen = complete_partial_with_penalty(env, s, zs, nju.weight)
+                # autograd: ONE forward kernel (box + Newton completion) and ONE backward kernel (GRG solve + nju . ineq_dist
+                # penalty + box derivative) between the policy sample and the critic (rpo_sac.py:324-334)
+                act_c, pen = complete_partial_squashed(env, box, s, zs, nju.weight, tanh=False)
                 qmin = critic(torch.cat([s, act_c], 1)).min(dim=1, keepdim=True).values
                 loss = (log_alpha.exp().detach() * logp - qmin + pen).mean()
                 # automatic temperature (rpo_sac.py:207-214); its gradient rides in the actor bucket's all-reduce
                 loss = loss - (log_alpha * (logp.detach() + target_entropy)).mean()
             else:
-                act_c, pen = complete_partial_with_penalty(env, s, policy(actor, s), nju.weight)   # rpo_ddpg.py:309-319
+                act_c, pen = complete_partial_squashed(env, box, s, actor(s), nju.weight, tanh=True)   # rpo_ddpg.py:309-319
                 loss = (-critic(torch.cat([s, act_c], 1)) + pen).mean()
             loss.backward()
 

@@ -105,6 +105,24 @@ int rpo_evopf_resid_bwd(const float* state, int ld_state, const float* y, const 
 int rpo_evopf_complete_bwd_penalty(const float* state, int ld_state, const float* y, const float* dl_dy, const float* w,
                                    const float* row_scale, float* dl_dz, float* dl_dx, int64_t B, void* stream);
 
+/* The action box fused into the completion / projection and into the GRG backward   rpo/algo/model/utils.py:40-51,75-101,
+ * rpo/algo/model/policy.py:30-31 (box(tanh(x), state)) followed by rpo/algo/rpo_ddpg.py:72-77 / evopf.py:724-727.
+ * u (B,14) = the policy's raw output; z = box(u) against the state-dependent EVOPF partial box (box_lo / box_hi: the 14
+ * constant bounds, whose last 5 entries are replaced by the battery bounds of the row's state of charge, exactly as
+ * rpo_box_fwd with n_vol = 5); box_mode 0-3 as rpo_box_fwd.  Results equal rpo_box_fwd -> rpo_evopf_project /
+ * rpo_evopf_complete_fwd bit for bit; the backward returns dL/du = dL/dz . d box / d u (rpo_box_bwd's arithmetic) and
+ * optionally folds the actor-loss penalty in as rpo_evopf_complete_bwd_penalty does (w nullable: no penalty). */
+int rpo_evopf_project_squashed(const float* state, int ld_state, const float* u, const float* box_lo, const float* box_hi,
+                               int box_mode, float* y, float* y_corr, int64_t B, float tol, int max_iters, float lr,
+                               float momentum, float corr_eps, int n_steps, int32_t* unsat_flags, int32_t* status,
+                               void* stream);
+int rpo_evopf_complete_fwd_squashed(const float* state, int ld_state, const float* u, const float* box_lo,
+                                    const float* box_hi, int box_mode, float* y, int64_t B, float tol, int max_iters,
+                                    int32_t* status, void* stream);
+int rpo_evopf_complete_bwd_squashed(const float* state, int ld_state, const float* y, const float* dl_dy, const float* u,
+                                    const float* box_lo, const float* box_hi, int box_mode, const float* w,
+                                    const float* row_scale, float* dl_du, float* dl_dx, int64_t B, void* stream);
+
 /* EVOPFEnv.step, batched row-wise                                rpo/env/electrical_grid/evopf.py:348-366 (+Battery.step :74-102, obj_fn :509-518)
  * state (B,57); y (B,43) action; next_exo (B,52) = next [pd|qd](28) + next price window (24) from the data loaders;
  * next_state (B,57) out; reward (B) out; eq_viol (B,28) nullable; ineq_viol (B,58) nullable (both at the pre-step state). */

@@ -32,6 +32,10 @@ SIGNATURES = {
     "rpo_evopf_resid": (c_int, [_P, c_int, _P, _P, _P, c_int64, _P]),
     "rpo_evopf_resid_bwd": (c_int, [_P, c_int, _P, _P, _P, c_int, _P, c_int64, _P]),
     "rpo_evopf_complete_bwd_penalty": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, c_int64, _P]),
+    "rpo_evopf_project_squashed": (c_int, [_P, c_int, _P, _P, _P, c_int, _P, _P, c_int64, c_float, c_int, c_float, c_float,
+                                           c_float, c_int, _P, _P, _P]),
+    "rpo_evopf_complete_fwd_squashed": (c_int, [_P, c_int, _P, _P, _P, c_int, _P, c_int64, c_float, c_int, _P, _P]),
+    "rpo_evopf_complete_bwd_squashed": (c_int, [_P, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, c_int64, _P]),
     "rpo_evopf_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "rpo_cart_complete_fwd": (c_int, [_P, _P, c_int64, c_int, _P]),
     "rpo_cart_complete_bwd": (c_int, [_P, _P, c_int64, c_int, _P]),

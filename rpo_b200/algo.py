@@ -91,6 +91,63 @@ def complete_partial_with_penalty(env, state, action_partial, nju_weight):
     return _CompletePenaltyFn.apply(state, action_partial, nju_weight, env.newton_tol, env.newton_max_iters)
 
 
+class _SquashedCompletePenaltyFn(torch.autograd.Function):
+    """box(u, state) -> complete_partial -> nju(ineq_dist) as one autograd node: forward = rpo_evopf_complete_fwd_squashed
+    (+ the residual kernel when a penalty is wanted), backward = ONE launch of rpo_evopf_complete_bwd_squashed (GRG
+    transposed solve with the penalty selector added in registers and the box derivative applied to the 14 reduced
+    gradients).  Replaces four launches and two (B,14) / (B,43) round trips of the unfused graph."""
+
+    @staticmethod
+    def forward(ctx, state, u, lo, hi, mode, weight, tol, max_iters):
+        from . import ops
+        y = ops.evopf_complete_fwd_squashed(state, u, lo, hi, mode, tol=tol, max_iters=max_iters)
+        ctx.mode = mode
+        if weight is None:
+            ctx.save_for_backward(state, u, lo, hi, y)
+            ctx.has_w = False
+            return y, y.new_zeros(y.shape[0], 1)
+        dist = torch.clamp_(ops.evopf_resid(state, y, want_eq=False, want_ineq=True)[1], 0)
+        ctx.save_for_backward(state, u, lo, hi, y, dist, weight)
+        ctx.has_w = True
+        return y, dist @ weight.reshape(-1, 1)
+
+    @staticmethod
+    def backward(ctx, dl_dy, dl_dpen):
+        from . import ops
+        if ctx.has_w:
+            state, u, lo, hi, y, dist, weight = ctx.saved_tensors
+        else:
+            state, u, lo, hi, y = ctx.saved_tensors
+            dist = weight = None
+        if dl_dy is None:
+            dl_dy = torch.zeros_like(y)
+        rs = None
+        if ctx.has_w:
+            rs = dl_dpen.contiguous() if dl_dpen is not None else torch.zeros(y.shape[0], 1, dtype=y.dtype, device=y.device)
+        du, dx = ops.evopf_complete_bwd_squashed(state, y, dl_dy.contiguous(), u, lo, hi, ctx.mode,
+                                                 None if weight is None else weight.detach(), rs, need_dx=ctx.needs_input_grad[0])
+        d_state = None
+        if ctx.needs_input_grad[0]:
+            d_state = torch.zeros_like(state)
+            d_state[:, :28] = dx
+        d_w = (rs.reshape(1, -1) @ dist).reshape(weight.shape) if (ctx.has_w and ctx.needs_input_grad[5]) else None
+        return d_state, du, None, None, None, d_w, None, None
+
+
+def complete_partial_squashed(env, box, state, u, nju_weight=None, tanh: bool = True):
+    """EVOPF: (action, penalty) = (complete_partial(state, box(tanh(u), state)), nju(ineq_dist)) with the action box of a
+    `rpo_b200.box.BoxConstraint` fused into the completion kernel and its derivative into the GRG backward kernel.
+    tanh=True: u is the policy's raw output (policy.py:30-31); tanh=False: u is already in [-1, 1] (style 'tanh' affine)."""
+    from . import ops
+    if box.style != "tanh" or not box.volatile:
+        raise ValueError("the fused form covers the volatile 'tanh'-style EVOPF partial box")
+    mode = ops.BOX_TANH if tanh else ops.BOX_AFFINE
+    if u.dim() == 1:
+        u = u.view(1, -1)
+    return _SquashedCompletePenaltyFn.apply(state, u, box.cmin_torch, box.cmax_torch, mode, nju_weight, env.newton_tol,
+                                            env.newton_max_iters)
+
+
 class RPOProjectionMixin(object):
     """Mix into (or patch onto) rpo.algo.RPODDPG / RPOSAC: same attribute names, same return conventions."""
 
@@ -131,6 +188,24 @@ class RPOProjectionMixin(object):
             if k < limit:
                 yc, _ = self.env.correct(state, y, lr, self.corr_momentum, self.corr_eps, k)
         return yc if train else (yc, k)
+
+
+def process_action_squashed(projector, box, state, u, train=True, tanh=True):
+    """process_action(state, box(tanh(u), state)) for no-grad call sites in ONE launch (rpo_evopf_project_squashed): the
+    rollout / critic-target projections of rpo_ddpg.py:96-106,327-332 with the policy's squash fused in."""
+    from . import ops
+    env = projector.env
+    lr, limit = (projector.corr_lr, projector.max_steps) if train else (projector.eval_lr, projector.eval_steps)
+    mode = ops.BOX_TANH if tanh else ops.BOX_AFFINE
+    yc, y, flags, _ = ops.evopf_project_squashed(state, u, box.cmin_torch, box.cmax_torch, mode, lr, projector.corr_momentum,
+                                                 projector.corr_eps, limit, tol=env.newton_tol, max_iters=env.newton_max_iters,
+                                                 want_y=projector.exact_loop_exit)
+    k = limit
+    if projector.exact_loop_exit:
+        k = reference_step_count(flags, limit)
+        if k < limit:
+            yc, _ = env.correct(state, y, lr, projector.corr_momentum, projector.corr_eps, k)
+    return yc if train else (yc, k)
 
 
 def install(rpo_module=None, register_envs: bool = True, box: bool = True):

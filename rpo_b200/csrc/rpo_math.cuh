@@ -110,6 +110,12 @@ RPO_HD void rpo_sincos_mixed(float x, double* sp, double* cp) {
     }
 }
 
+// next representable `real` above / below x (the reduced cart correction walks to a rounding boundary with it)
+RPO_HD float rpo_next(float x, bool up) { return nextafterf(x, up ? 3.0e38f : -3.0e38f); }
+#if !defined(__CUDA_ARCH__)
+static inline double rpo_next(double x, bool up) { return nextafter(x, up ? 1.0e300 : -1.0e300); }
+#endif
+
 #if defined(__CUDA_ARCH__)
 // device, float only (the CUDA build is always float)
 RPO_D float rpo_rcp_approx(float x) {

@@ -196,6 +196,72 @@ def evopf_complete_bwd_penalty(state, y, dl_dy, w, row_scale=None, need_dx: bool
     return dz, dx
 
 
+def _box14(lo, hi):
+    lo, hi = _dev(lo, "box_lo").view(-1), _dev(hi, "box_hi").view(-1)
+    if lo.numel() != 14 or hi.numel() != 14:
+        raise ValueError("the EVOPF partial-action box has 14 bounds")
+    return lo, hi
+
+
+def evopf_project_squashed(state, u, lo, hi, box_mode: int, lr: float, momentum: float, corr_eps: float, n_steps: int,
+                           tol: float = 1e-5, max_iters: int = 50, want_y: bool = False, want_flags: bool = True,
+                           want_status: bool = False):
+    """evopf_project(state, box(u), ...) in ONE launch: the action box (rpo_box_fwd, n_vol = 5) is applied inside the
+    projection kernel; bit-identical to box_fwd -> evopf_project."""
+    lib = _lib.load()
+    state, ld = _rows(state, "state", 33)
+    u = _dev(u, "u", 14)
+    lo, hi = _box14(lo, hi)
+    B = u.shape[0]
+    _same_batch(B, state=state)
+    y = torch.empty(B, 43, dtype=torch.float32, device=u.device) if want_y else None
+    yc = torch.empty(B, 43, dtype=torch.float32, device=u.device)
+    flags = torch.empty(max(n_steps, 1), dtype=torch.int32, device=u.device) if want_flags else None
+    status = torch.empty(B, dtype=torch.int32, device=u.device) if want_status else None
+    with torch.cuda.device(u.device):
+        _lib.check(lib.rpo_evopf_project_squashed(state.data_ptr(), ld, u.data_ptr(), lo.data_ptr(), hi.data_ptr(), box_mode,
+                                                  _ptr(y), yc.data_ptr(), B, tol, max_iters, lr, momentum, corr_eps, n_steps,
+                                                  _ptr(flags), _ptr(status), _stream(u)), "rpo_evopf_project_squashed")
+    return yc, y, flags, status
+
+
+def evopf_complete_fwd_squashed(state, u, lo, hi, box_mode: int, tol: float = 1e-5, max_iters: int = 50):
+    lib = _lib.load()
+    state, ld = _rows(state, "state", 33)
+    u = _dev(u, "u", 14)
+    lo, hi = _box14(lo, hi)
+    B = u.shape[0]
+    _same_batch(B, state=state)
+    y = torch.empty(B, 43, dtype=torch.float32, device=u.device)
+    with torch.cuda.device(u.device):
+        _lib.check(lib.rpo_evopf_complete_fwd_squashed(state.data_ptr(), ld, u.data_ptr(), lo.data_ptr(), hi.data_ptr(), box_mode,
+                                                       y.data_ptr(), B, tol, max_iters, None, _stream(u)),
+                   "rpo_evopf_complete_fwd_squashed")
+    return y
+
+
+def evopf_complete_bwd_squashed(state, y, dl_dy, u, lo, hi, box_mode: int, w=None, row_scale=None, need_dx: bool = False):
+    """dL/du (and dL/dx) of the squashed completion, optionally with the nju . ineq_dist penalty folded in (one launch)."""
+    lib = _lib.load()
+    state, ld = _rows(state, "state", 33)
+    y = _dev(y, "y", 43)
+    dl_dy = _dev(dl_dy, "dl_dy", 43)
+    u = _dev(u, "u", 14)
+    lo, hi = _box14(lo, hi)
+    w = None if w is None else _dev(w, "w", 58)
+    B = y.shape[0]
+    if row_scale is not None:
+        row_scale = _dev(row_scale.reshape(-1, 1), "row_scale", 1)
+    _same_batch(B, state=state, dl_dy=dl_dy, u=u, row_scale=row_scale)
+    du = torch.empty(B, 14, dtype=torch.float32, device=y.device)
+    dx = torch.empty(B, 28, dtype=torch.float32, device=y.device) if need_dx else None
+    with torch.cuda.device(y.device):
+        _lib.check(lib.rpo_evopf_complete_bwd_squashed(state.data_ptr(), ld, y.data_ptr(), dl_dy.data_ptr(), u.data_ptr(),
+                                                       lo.data_ptr(), hi.data_ptr(), box_mode, _ptr(w), _ptr(row_scale),
+                                                       du.data_ptr(), _ptr(dx), B, _stream(y)), "rpo_evopf_complete_bwd_squashed")
+    return du, dx
+
+
 def evopf_step(state, y, next_exo, want_viol: bool = True):
     lib = _lib.load()
     state = _dev(state, "state", 57)

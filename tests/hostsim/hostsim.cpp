@@ -121,6 +121,21 @@ void hs_cart_correct(real* a, int B, int p, real lr, real momentum, real eps, in
             if (cart_correct_step<true>(k, a + 2 * (long)b, prev, lr, momentum, eps) && flags) flags[s] = 1;
     }
 }
+// reduced-form correction loop (the kernels' fast path), for the bit-exactness test against hs_cart_correct
+void hs_cart_correct_red(real* a, int B, int p, real lr, real momentum, real eps, int n_steps, int* flags) {
+    const CartK k = cart_constants(p);
+    const CartRed r = cart_reduced(k);
+    for (int b = 0; b < B; ++b) {
+        real ap = a[2 * (long)b + p], ao = a[2 * (long)b + 1 - p], pp = 0, po = 0;
+        for (int s = 0; s < n_steps; ++s)
+            if (cart_correct_step_red<true, true>(k, r, ap, ao, pp, po, lr, momentum, eps) && flags) flags[s] = 1;
+        a[2 * (long)b + p] = ap; a[2 * (long)b + 1 - p] = ao;
+    }
+}
+void hs_cart_thresholds(int p, real* t, real* A) {
+    const CartRed r = cart_reduced(cart_constants(p));
+    for (int j = 0; j < 3; ++j) { t[j] = r.t[j]; A[j] = r.A[j]; }
+}
 void hs_cart_resid(const real* a, real* eq, real* ineq, int B) {
     const CartK k = cart_constants(0);
     for (int b = 0; b < B; ++b) {

@@ -278,6 +278,24 @@ def box_bwd(x, grad_out, lo, hi, mode=0, state=None, n_vol=0):
     return _box(True, x, grad_out, lo, hi, mode, state, n_vol, None)
 
 
+def evopf_project_squashed(state, u, lo, hi, box_mode, lr, momentum, corr_eps, n_steps, tol=1e-5, max_iters=50, want_y=False,
+                           want_flags=True, want_status=False):
+    z = box_fwd(u, lo, hi, box_mode, state, 5)
+    return evopf_project(state, z, lr, momentum, corr_eps, n_steps, tol, max_iters, want_y, want_flags, want_status)
+
+
+def evopf_complete_fwd_squashed(state, u, lo, hi, box_mode, tol=1e-5, max_iters=50):
+    return evopf_complete_fwd(state, box_fwd(u, lo, hi, box_mode, state, 5), tol, max_iters)
+
+
+def evopf_complete_bwd_squashed(state, y, dl_dy, u, lo, hi, box_mode, w=None, row_scale=None, need_dx=False):
+    if w is None:
+        dz, dx = evopf_complete_bwd(y, dl_dy, need_dx)
+    else:
+        dz, dx = evopf_complete_bwd_penalty(state, y, dl_dy, w, row_scale, need_dx)
+    return box_bwd(u, dz, lo, hi, box_mode, state, 5), dx
+
+
 NAMES = [n for n in dir() if n.startswith(("evopf_", "cart_", "pen_", "box_"))]
 
 

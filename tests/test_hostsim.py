@@ -220,3 +220,36 @@ def test_refined_completion_residual_is_below_the_float32_reference(libs, dist, 
     assert rel_err(torch.as_tensor(y_r), y_ref).max() <= 2e-5
     # the refinement replaces Newton iterations, it does not add to them: applied updates per instance (self vote)
     assert (status_r & 0xff).mean() <= (status_p & 0xff).mean() + 0.5
+
+
+@pytest.mark.parametrize("p", [0, 1])
+def test_cart_reduced_correction_step_is_bit_identical_to_the_row_form(libs, p):
+    """The K-step cart kernels run cart_correct_step_red (3 compares on |a_p| against rounding boundaries found from the
+    fused test itself, pairwise |.| in the loop test); it must reproduce the row-by-row form of cartpole.py:396-408 bit
+    for bit — including on the floats adjacent to every boundary, with momentum, and when a large step overshoots."""
+    lib = libs["f32"]
+    f = ctypes.c_float
+    rng = np.random.default_rng(p)
+    t, A = np.zeros(3, np.float32), np.zeros(3, np.float32)
+    lib.hs_cart_thresholds(p, _P(t), _P(A))
+    assert (A > 0).all() and (t > 0).all()
+    B = 200000
+    z = rng.uniform(-14, 14, B).astype(np.float32)
+    pos = 0
+    for j in range(3):                                   # 40 floats on each side of +-t_j
+        for sgn in (1.0, -1.0):
+            for away in (100.0, 0.0):
+                v = np.float32(sgn * t[j])
+                for _ in range(40):
+                    z[pos] = v
+                    pos += 1
+                    v = np.nextafter(v, np.float32(sgn * away), dtype=np.float32)
+    a = np.zeros((B, 2), np.float32)
+    lib.hs_cart_complete(_P(z), _P(a), B, p)
+    for lr, mom, K in ((2e-2, 0.0, 10), (2e-2, 0.5, 7), (0.3, 0.0, 50)):
+        a1, a2 = a.copy(), a.copy()
+        f1, f2 = np.zeros(64, np.int32), np.zeros(64, np.int32)
+        lib.hs_cart_correct(_P(a1), B, p, f(lr), f(mom), f(1e-5), K, _P(f1))
+        lib.hs_cart_correct_red(_P(a2), B, p, f(lr), f(mom), f(1e-5), K, _P(f2))
+        assert np.array_equal(a1.view(np.uint32), a2.view(np.uint32)) and np.array_equal(f1, f2)
+        assert np.abs(a1 - a).max() > 0.1
