@@ -62,6 +62,11 @@ def main():
     ap.add_argument("--policy-fre", type=int, default=4)
     ap.add_argument("--algo", choices=("ddpg", "sac"), default="ddpg")
     ap.add_argument("--graph", action="store_true", help="capture the training iteration in CUDA graphs (SURVEY f-3)")
+    ap.add_argument("--graph-full", action="store_true",
+                    help="with --graph: ONE graph per iteration, the two NCCL all-reduces captured inside it")
+    ap.add_argument("--profile", type=int, default=0, metavar="N",
+                    help="rank 0: torch.profiler (CUPTI) kernel table of N iterations after the timed loop -> --profile-out")
+    ap.add_argument("--profile-out", default="gpurun_out/train_profile.md")
     a = ap.parse_args()
     rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(local)
@@ -204,12 +209,21 @@ def main():
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize()
         graphs, pool = {}, torch.cuda.graph_pool_handle()
-        for key, fn, args in (("rc", seg_rollout_critic, ()), ("cs1", seg_critic_step, (True,)), ("cs0", seg_critic_step, (False,)),
-                              ("as", seg_actor_step, ())):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=pool):
-                fn(*args)
-            graphs[key] = g
+        if a.graph_full:
+            # the whole iteration, collectives included, as one graph per variant.  capture_error_mode="thread_local": NCCL's
+            # watchdog thread polls CUDA events, which a GLOBAL-mode capture forbids process-wide (the round-1 trial hung there)
+            for key, flag in (("it1", True), ("it0", False)):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool, capture_error_mode="thread_local"):
+                    iteration(flag)
+                graphs[key] = g
+        else:
+            for key, fn, args in (("rc", seg_rollout_critic, ()), ("cs1", seg_critic_step, (True,)), ("cs0", seg_critic_step, (False,)),
+                                  ("as", seg_actor_step, ())):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    fn(*args)
+                graphs[key] = g
 
         def run_graph(fn, *args):
             key = {seg_rollout_critic: "rc", seg_actor_step: "as"}.get(fn) or ("cs1" if args[0] else "cs0")
@@ -220,9 +234,16 @@ def main():
     n_proj = 0
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for it in range(a.iters):
+    def one(it):
         do_actor = it % a.policy_fre == 0
-        iteration(do_actor, run_graph if graphs is not None else None)
+        if graphs is not None and a.graph_full:
+            graphs["it1" if do_actor else "it0"].replay()
+        else:
+            iteration(do_actor, run_graph if graphs is not None else None)
+        return do_actor
+
+    for it in range(a.iters):
+        do_actor = one(it)
         n_proj += a.envs + a.batch + (a.batch if do_actor else 0)
     rew = last_rew
     torch.cuda.synchronize()
@@ -240,12 +261,44 @@ def main():
         n_all = float(tot.item())
     else:
         n_all = float(n_proj)
+    if a.profile:                                        # CUPTI kernel table of N iterations (rank 0 writes it; all ranks run them)
+        from torch.profiler import ProfilerActivity, profile
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            for it in range(a.profile):
+                one(it)
+            torch.cuda.synchronize()
+        if rank == 0:
+            rows = [(e.key, e.count, e.device_time_total) for e in prof.key_averages() if e.device_time_total > 0 and e.device_type.name == "CUDA"]
+            if not rows:
+                rows = [(e.key, e.count, e.device_time_total) for e in prof.key_averages() if e.device_time_total > 0]
+            tot = sum(r[2] for r in rows) or 1.0
+            rows.sort(key=lambda r: -r[2])
+            os.makedirs(os.path.dirname(a.profile_out) or ".", exist_ok=True)
+            with open(a.profile_out, "w") as fh:
+                fh.write("# kernel table of %d training iterations (%s, world %d, %s), rank 0, torch.profiler / CUPTI\n\n" %
+                         (a.profile, a.algo, world, "CUDA graphs%s" % (" incl. collectives" if a.graph_full else "") if a.graph else "eager"))
+                fh.write("flat gradient buckets: critic %d B, actor+nju%s %d B\n\n" % (b_critic.flat.numel() * 4, "+log_alpha" if sac else "", b_actor.flat.numel() * 4))
+                fh.write("| kernel | launches | total us | share |\n|---|---|---|---|\n")
+                for k, c, t in rows[:40]:
+                    fh.write("| `%s` | %d | %.1f | %.1f %% |\n" % (k[:110], c, t, 100.0 * t / tot))
+                fh.write("\nGPU time of all kernels: %.1f us over %d iterations = %.1f us / iteration\n" % (tot, a.profile, tot / a.profile))
     if rank == 0:
         print(json.dumps({"world": world, "iters": a.iters, "envs_per_gpu": a.envs, "batch_per_gpu": a.batch,
-                          "algo": a.algo, "cuda_graph": bool(a.graph), "iters_per_s": a.iters / dt, "projected_actions_per_s": n_all / dt,
+                          "algo": a.algo, "cuda_graph": bool(a.graph), "collectives_in_graph": bool(a.graph and a.graph_full), "iters_per_s": a.iters / dt, "projected_actions_per_s": n_all / dt,
                           "env_steps_per_s": world * a.envs * a.iters / dt, "max_replica_drift": float(drift.item()),
                           "final_reward_mean": float(rew.mean()), "finite": bool(torch.isfinite(w).all())}))
     if world > 1:
+        if a.graph and a.graph_full:
+            # graphs that captured NCCL kernels keep the communicator busy: release them before tearing it down (the first
+            # trial hung in destroy_process_group), and do not wait for NCCL's own teardown
+            sys.stdout.flush()
+            graphs.clear()
+            import gc
+            gc.collect()
+            torch.cuda.synchronize()
+            dist.barrier()
+            os._exit(0)
         dist.destroy_process_group()
 
 

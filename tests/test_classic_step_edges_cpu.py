@@ -65,3 +65,65 @@ def test_pendulum_step_edges():
             assert bool(done[i]) == done_r, i
         np.testing.assert_allclose(iqv[i].numpy(), np.ravel(info["ineq_viol"]), rtol=2e-6, atol=1e-5)
         np.testing.assert_allclose(eqv[i].numpy(), np.ravel(info["eq_viol"]), rtol=2e-5, atol=2e-5)
+
+
+def test_multi_step_trajectories_of_the_scalar_gym_api_follow_the_reference(monkeypatch):
+    """the drop-in `step()` keeps its persistent state through the kernels' float32 I/O (the reference keeps
+    python floats / float64).  Over whole episodes with a fixed action sequence the drift this causes stays at float32
+    round-off of the state: the drop-in CartSafeEnv / SpringPendulumEnv / EVOPFEnv trajectories track the unmodified
+    reference's step for step, and the episodes end on the same step."""
+    import os
+    from oracle.ref_loader import DATA_DIR, make_cpu_env
+    from tests import hostsim_ops
+    hostsim_ops.install(monkeypatch)
+    from rpo_b200.env import CartSafeEnv, EVOPFEnv, SpringPendulumEnv
+    rng = np.random.default_rng(11)
+    # cart: stabilising-ish random forces for up to 200 steps
+    ref, env = make_cpu_env("cart"), CartSafeEnv(device="cpu", partial_idx=0)
+    s0 = rng.uniform(-0.05, 0.05, size=6)
+    ref.reset(); env.reset()
+    ref.state, env.state = tuple(s0), tuple(s0)
+    ref.steps_beyond_done = env.steps_beyond_done = None
+    worst = 0.0
+    for t in range(200):
+        a = rng.uniform(-3, 3, size=2).astype(np.float32)
+        o_r, r_r, d_r, _ = ref.step(a.copy())
+        o_b, r_b, d_b, _ = env.step(a.copy())
+        worst = max(worst, float(np.abs(np.asarray(o_b) - np.asarray(o_r)).max() / max(1.0, np.abs(o_r).max())))
+        assert d_r == d_b and r_r == r_b, t
+        if d_r:
+            break
+    assert t >= 5 and worst < 2e-5, (t, worst)
+    # pendulum
+    ref, env = make_cpu_env("pen"), SpringPendulumEnv(device="cpu")
+    ref.reset(); env.reset()
+    st0 = np.array([0.05, -0.2, 1.01, 0.01])
+    ref.state, env.state = st0.copy(), st0.copy()
+    worst = 0.0
+    for t in range(200):
+        a = rng.uniform(-2, 2, size=2).astype(np.float32) + np.array([0.0, 5.0], np.float32)     # roughly holds the weight
+        o_r, r_r, d_r, _ = ref.step(a.copy())
+        o_b, r_b, d_b, _ = env.step(a.copy())
+        worst = max(worst, float(np.abs(np.asarray(o_b) - np.asarray(o_r)).max()))
+        assert d_r == d_b, t
+        assert abs(r_r - r_b) <= 1e-3 * max(1.0, abs(r_r))
+        if d_r:
+            break
+    assert t >= 5 and worst < 5e-5, (t, worst)
+    # EVOPF: a whole 24-step day, state of charge accumulating through the battery efficiency
+    np.random.seed(5)
+    ref = make_cpu_env("evopf")
+    np.random.seed(5)
+    env = EVOPFEnv(device="cpu", data_dir=DATA_DIR)
+    np.random.seed(6); s_r = ref.reset()
+    np.random.seed(6); s_b = env.reset()
+    assert np.abs(s_r - s_b).max() < 1e-12
+    for t in range(24):
+        a = ref.action_space.sample().astype(np.float32)
+        a[38:] = rng.uniform(-0.25, 0.25, size=5)                         # battery power beyond its box: clipped by Battery.step
+        ns_r, r_r, d_r, i_r = ref.step(a.copy())
+        ns_b, r_b, d_b, i_b = env.step(a.copy())
+        assert d_r == d_b
+        assert np.abs(ns_b - ns_r).max() < 2e-6, (t, np.abs(ns_b - ns_r).max())       # soc drift stays at float32 round-off
+        assert abs(r_r - r_b) <= 2e-5 * max(1.0, abs(r_r))
+    assert d_r
