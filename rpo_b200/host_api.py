@@ -52,6 +52,28 @@ class HostProjector(object):
         self.d2h_bytes = 0
         self.launches = 0
 
+    def _schedule(self, B: int):
+        """Row ranges of the chunks.  The pipeline's fill (first chunk's upload, nothing to overlap with) and drain (last
+        chunk's kernels + download) are pure latency, so the batch is cut small at both ends — chunk/4, chunk/2, chunk, ...,
+        chunk, chunk/2, chunk/4 — when it is large enough for that to matter."""
+        c = self.chunk
+        if B < 6 * c or c < 4096:
+            return [(b0, min(B, b0 + c)) for b0 in range(0, B, c)]
+        head = [c // 4, c // 2]
+        out, b0 = [], 0
+        for n in head:
+            out.append((b0, b0 + n))
+            b0 += n
+        tail = sum(head)
+        while B - tail - b0 > 0:
+            n = min(c, B - tail - b0)
+            out.append((b0, b0 + n))
+            b0 += n
+        for n in reversed(head):
+            out.append((b0, b0 + n))
+            b0 += n
+        return out
+
     @staticmethod
     def pinned(*shape, dtype=torch.float32):
         return torch.empty(*shape, dtype=dtype, pin_memory=True)
@@ -70,8 +92,7 @@ class HostProjector(object):
             s.wait_stream(cur)
         self.h2d_bytes = self.d2h_bytes = self.launches = 0
         with torch.cuda.device(self.device):
-            for i, b0 in enumerate(range(0, B, self.chunk)):
-                b1 = min(B, b0 + self.chunk)
+            for i, (b0, b1) in enumerate(self._schedule(B)):
                 n = b1 - b0
                 s = self.streams[i % len(self.streams)]
                 slot = self.slots[i % len(self.slots)]
