@@ -12,6 +12,9 @@
  *     `ld_state` (in floats) so that a (B,57) observation tensor or a (B,28) [pd|qd] slice can be passed;
  *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream, allocates
  *     nothing and never synchronises;
+ *   - alignment: 4 bytes is enough for the EVOPF entry points, the action box and rpo_cart_correct / rpo_cart_project
+ *     (they take vector / TMA paths only when the pointers allow); the single-pass cart / pendulum entry points need their
+ *     (B,2) arrays 8-byte aligned and the pendulum's (B,4) states 16-byte aligned and return RPO_ERR_INVALID_ARG otherwise;
  *   - return value 0 = ok, negative = error (RPO_ERR_*); rpo_last_error() gives a message;
  *   - a pointer documented "nullable" may be NULL to skip that output.
  */

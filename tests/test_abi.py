@@ -122,3 +122,32 @@ def test_box_argument_validation_without_gpu(built):
     assert lib.rpo_box_fwd(None, P, P, 14, P, 57, 5, P, 0, 4, None) == -1          # x missing for an x-mode
     assert lib.rpo_box_bwd(P, P, P, P, 14, P, 57, 5, P, 4, 4, None) == -1          # no backward for the query modes
     assert lib.rpo_box_fwd(P, P, P, 14, P, 57, 5, P, 0, 0, None) == 0              # empty batch
+
+
+def test_round2_entry_points_validate_their_arguments_without_gpu(built):
+    """Argument checks of the entry points added in round 2 run before any CUDA call: exercised here without a GPU."""
+    lib = built.load()
+    A = 0x1000                                                # a 16-byte aligned non-null pointer value (never dereferenced)
+    # alignment contract of the single-pass classic entry points (ADVICE r1: float2 / float4 accesses)
+    assert lib.rpo_cart_direction(A + 4, A, 8, 0, None) == -1 and b"8-byte aligned" in lib.rpo_last_error()
+    assert lib.rpo_cart_resid(A + 4, A, A, 8, None) == -1
+    assert lib.rpo_cart_complete_bwd(A + 4, A, 8, 1, None) == -1
+    assert lib.rpo_pen_step(A + 8, A, A, A, A, A, None, None, 8, None) == -1 and b"16-byte aligned" in lib.rpo_last_error()
+    assert lib.rpo_pen_project(A, A, A + 4, A, 8, 2e-3, 0.0, 1e-5, 10, None, None) == -1
+    # residual backward / fused backward
+    assert lib.rpo_evopf_resid_bwd(A, 57, A, None, A, 2, A, 8, None) == -1 and b"ineq_mode" in lib.rpo_last_error()
+    assert lib.rpo_evopf_resid_bwd(A, 20, A, A, None, 0, A, 8, None) == -1 and b"ld_state" in lib.rpo_last_error()
+    assert lib.rpo_evopf_resid_bwd(None, 57, A, A, None, 0, A, 8, None) == -1
+    assert lib.rpo_evopf_complete_bwd_penalty(A, 57, A, A, None, None, A, None, 8, None) == -1          # dual weights missing
+    assert lib.rpo_evopf_complete_bwd_penalty(A, 30, A, A, A, None, A, None, 8, None) == -1             # no state of charge in the row
+    assert lib.rpo_evopf_complete_bwd_squashed(A, 57, A, A, A, A, A, 5, None, None, A, None, 8, None) == -1 and b"box mode" in lib.rpo_last_error()
+    assert lib.rpo_evopf_complete_bwd_squashed(A, 57, A, A, None, A, A, 1, None, None, A, None, 8, None) == -1
+    assert lib.rpo_evopf_project_squashed(A, 57, A, None, A, 1, None, A, 8, 1e-5, 50, 1e-4, 0.0, 1e-5, 10, None, None, None) == -1
+    assert lib.rpo_evopf_project_squashed(A, 30, A, A, A, 1, None, A, 8, 1e-5, 50, 1e-4, 0.0, 1e-5, 10, None, None, None) == -1
+    assert lib.rpo_evopf_complete_fwd_squashed(A, 57, A, A, A, 7, A, 8, 1e-5, 50, None, None) == -1
+    assert lib.rpo_evopf_complete_fwd_plain(A, 20, A, A, 8, 1e-5, 50, None, None) == -1
+    assert lib.rpo_cart_resid_bwd(None, A, A, 0, A, 8, None) == -1                                      # g_ineq needs the action
+    assert lib.rpo_pen_resid_bwd(A, A, A, None, 3, A, 8, None) == -1
+    # empty batches are a no-op everywhere
+    assert lib.rpo_evopf_resid_bwd(A, 57, A, A, A, 1, A, 0, None) == 0
+    assert lib.rpo_evopf_complete_bwd_squashed(A, 57, A, A, A, A, A, 1, None, None, A, None, 0, None) == 0
