@@ -253,3 +253,40 @@ def test_cart_reduced_correction_step_is_bit_identical_to_the_row_form(libs, p):
         lib.hs_cart_correct_red(_P(a2), B, p, f(lr), f(mom), f(1e-5), K, _P(f2))
         assert np.array_equal(a1.view(np.uint32), a2.view(np.uint32)) and np.array_equal(f1, f2)
         assert np.abs(a1 - a).max() > 0.1
+
+
+def test_residual_vjp_against_finite_differences_in_float64(libs):
+    """evopf_eq_vjp / evopf_ineq_vjp (the autograd of eq_resid / ineq_resid / ineq_dist the kernels implement) in the float64
+    build of the generated code against central finite differences of the float64 residual functions themselves:
+    (d r / d y)^T g for random g, every one of the 43 action components."""
+    from rpo_b200 import synth
+    lib = libs["f64"]
+    B = 6
+    st = synth.evopf_states(B, seed=41).double().numpy().copy()
+    z = synth.evopf_partial_actions(torch.tensor(st).float(), seed=42).double().numpy().copy()
+    y, _ = _complete(lib, st, z, np.float64, ctypes.c_double, tol=1e-12)
+    rng = np.random.default_rng(43)
+    y = y + 0.01 * rng.standard_normal(y.shape)                # off the solution manifold, away from the inequality kinks
+    ge, gi = rng.standard_normal((B, 28)), rng.standard_normal((B, 58))
+
+    def resid(yy):
+        eq, iq = np.zeros((B, 28)), np.zeros((B, 58))
+        lib.hs_evopf_resid(_P(st), st.shape[1], _P(np.ascontiguousarray(yy)), _P(eq), _P(iq), B)
+        return eq, iq
+
+    eq0, iq0 = resid(y)
+    assert np.abs(iq0).min() > 1e-5                              # no inequality row sits on its kink
+    for mode in (0, 1):
+        dy = np.zeros((B, 43))
+        lib.hs_evopf_resid_bwd(_P(st), st.shape[1], _P(y), _P(ge), _P(gi), mode, _P(dy), B)
+        fd = np.zeros((B, 43))
+        h = 1e-6
+        for j in range(43):
+            yp, ym = y.copy(), y.copy()
+            yp[:, j] += h
+            ym[:, j] -= h
+            (ep, ip), (em, im) = resid(yp), resid(ym)
+            if mode == 1:
+                ip, im = np.maximum(ip, 0), np.maximum(im, 0)
+            fd[:, j] = (((ep - em) * ge).sum(1) + ((ip - im) * gi).sum(1)) / (2 * h)
+        assert np.abs(dy - fd).max() <= 1e-7 * max(1.0, np.abs(fd).max()), (mode, np.abs(dy - fd).max())
