@@ -290,3 +290,27 @@ def test_residual_vjp_against_finite_differences_in_float64(libs):
                 ip, im = np.maximum(ip, 0), np.maximum(im, 0)
             fd[:, j] = (((ep - em) * ge).sum(1) + ((ip - im) * gi).sum(1)) / (2 * h)
         assert np.abs(dy - fd).max() <= 1e-7 * max(1.0, np.abs(fd).max()), (mode, np.abs(dy - fd).max())
+
+
+def test_cart_reduced_step_bit_identity_on_arbitrary_float_bit_patterns(libs):
+    """Same property over the whole float32 range: random bit patterns for both forces (denormals, huge values, +-0, inf,
+    NaN included), fed to the correction loops directly — the reduced form must equal the row form bit for bit, and raise
+    the same loop-test flags."""
+    lib = libs["f32"]
+    f = ctypes.c_float
+    rng = np.random.default_rng(99)
+    B = 300000
+    bits = rng.integers(0, 2 ** 32, size=(B, 2), dtype=np.uint64).astype(np.uint32)
+    a = bits.view(np.float32).copy()
+    a[:1000] = rng.uniform(-12, 12, size=(1000, 2)).astype(np.float32)
+    a[1000:1008] = np.array([[0.0, -0.0], [-0.0, 0.0], [np.inf, 1.0], [-np.inf, 1.0], [np.nan, 1.0], [1.0, np.nan],
+                             [3.4e38, -3.4e38], [1e-45, -1e-45]], np.float32)
+    for p in (0, 1):
+        for lr, mom, K in ((2e-2, 0.0, 10), (2e-2, 0.9, 4)):
+            a1, a2 = a.copy(), a.copy()
+            f1, f2 = np.zeros(64, np.int32), np.zeros(64, np.int32)
+            lib.hs_cart_correct(_P(a1), B, p, f(lr), f(mom), f(1e-5), K, _P(f1))
+            lib.hs_cart_correct_red(_P(a2), B, p, f(lr), f(mom), f(1e-5), K, _P(f2))
+            same = (a1.view(np.uint32) == a2.view(np.uint32)) | (np.isnan(a1) & np.isnan(a2))
+            assert same.all(), (p, lr, mom, a[~same.all(1)][:4], a1[~same.all(1)][:4], a2[~same.all(1)][:4])
+            assert np.array_equal(f1, f2)
